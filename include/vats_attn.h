@@ -1,0 +1,145 @@
+/*
+ * vats_attn.h — C-ABI of the B200 (sm_100a) GQA + sliding-window attention core.
+ *
+ * This is the drop-in boundary for the one hot path of S-VATS31/vats-multimodal-lm that the LLM,
+ * the 2D ViT and the 3D ViT share.  The reference has no FFI of its own: its boundary is a single
+ * library call, `F.scaled_dot_product_attention`, made from three modules.  Every entry point below
+ * names the reference call site it replaces (paths relative to the reference tree):
+ *
+ *   vats_attn_prefill        src/optimized_attention.py:657-723            (LLM  Attention.forward SDPA branch, incl. the
+ *                                                                           mask build at 668-706 and `extend_kv_heads` 486-497)
+ *                            src/optimized_attention.py:628-635            (the intended FA2 call: causal + window_size=(left,right))
+ *                            src/transformers/vision/vit_2d/optimized_attention.py:348-423   (SpatialAttention._torch_attention)
+ *                            src/transformers/vision/vit_3d/optimized_attention.py:185-348   (_grouped_query_attention, spatial and temporal)
+ *   vats_attn_decode         src/optimized_attention.py:508-516 + 709-714  (the intended KV-cache single-query step; the cache
+ *                                                                           type is KVCache, src/optimized_attention.py:169-287)
+ *   vats_attn_debug_mask     the mask predicate of SURVEY.md §8a-0 (src/optimized_attention.py:519-520, 632-634, 673-675;
+ *                            vit_3d/optimized_attention.py:276-277) materialised for bit-exact tests
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to bf16 (uint16 storage) unless stated otherwise.
+ *   - Strides are in ELEMENTS, ordered (sequence, token, head); the head_dim axis is contiguous (stride 1).
+ *   - K/V carry G (= query_groups) heads and are never expanded: query head h reads K/V head h / (H/G)
+ *     (the `repeat_interleave` ordering of utils/attention_utils.py:27).  G == 1 is the MQA case.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Return value 0 = success; non-zero = error, message available from vats_attn_last_error() (thread-local).
+ *   - There is NO CPU fallback and no other backend: a missing GPU, a non-sm_100 device or an unsupported
+ *     geometry is an error.
+ *   - The caller owns every buffer, including the decode workspace.
+ *
+ * Mask predicate (normative; `off = Tk - Tq`, bottom-right aligned):
+ *   allowed(n,i,j) = (q_valid == NULL || q_valid[n*Tq+i]) && (k_valid == NULL || k_valid[n*Tk+j])
+ *                 && (!causal  || j <= i + off)
+ *                 && (left  < 0 || j >= i + off - left)
+ *                 && (right < 0 || j <= i + off + right)
+ *   A query row with no allowed key produces an all-zero output row (never NaN).
+ */
+#ifndef VATS_ATTN_H_
+#define VATS_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VATS_ATTN_VERSION 100 /* major*100 + minor */
+
+/* error codes */
+#define VATS_OK 0
+#define VATS_ERR_INVALID_ARGUMENT 1
+#define VATS_ERR_UNSUPPORTED 2 /* geometry / layout / device the kernels do not cover */
+#define VATS_ERR_CUDA 3        /* a CUDA runtime / driver call failed */
+#define VATS_ERR_WORKSPACE 4   /* decode workspace missing or too small */
+
+/* kernel selector for vats_attn_prefill_ex */
+#define VATS_KERNEL_AUTO 0    /* shape-based choice (what vats_attn_prefill uses) */
+#define VATS_KERNEL_TCGEN05 1 /* TMA + tcgen05/TMEM tile kernel; error if the geometry is not TMA-legal */
+#define VATS_KERNEL_SIMT 2    /* CUDA-core warp kernel for tiny / irregular sequences */
+
+/*
+ * Prefill / encoder attention:  O[n,i,h,:] = softmax_j( scale * <Q[n,i,h,:], K[n,j,h/(H/G),:]> | allowed ) . V[n,j,h/(H/G),:]
+ *
+ *   q,o      [N, Tq, H, hd]   k,v  [N, Tk, G, hd]     (any strides; hd contiguous)
+ *   q_valid  [N, Tq] uint8 or NULL  — LLM SDPA-path padding semantics (query rows), src/optimized_attention.py:673-675
+ *   k_valid  [N, Tk] uint8 or NULL  — ViT-3D key-padding semantics, vit_3d/optimized_attention.py:276-277
+ *   scale    softmax scale applied to the logits (reference: self.softmax_scale or 1/sqrt(hd))
+ *   causal   non-zero = causal; the caller applies the reference's `if causal: right_window = 0` itself or not —
+ *            the predicate above makes both spellings equivalent.
+ *   left/right  window; negative = unlimited.
+ */
+int vats_attn_prefill(const void* q, const void* k, const void* v, void* o,
+                      const uint8_t* q_valid, const uint8_t* k_valid,
+                      int N, int Tq, int Tk, int H, int G, int hd,
+                      const int64_t q_strides[3], const int64_t k_strides[3],
+                      const int64_t v_strides[3], const int64_t o_strides[3],
+                      float scale, int causal, int left, int right, void* stream);
+
+/* Same, with an explicit kernel choice (VATS_KERNEL_*).  Used by tests to cross-check the two kernels. */
+int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o,
+                         const uint8_t* q_valid, const uint8_t* k_valid,
+                         int N, int Tq, int Tk, int H, int G, int hd,
+                         const int64_t q_strides[3], const int64_t k_strides[3],
+                         const int64_t v_strides[3], const int64_t o_strides[3],
+                         float scale, int causal, int left, int right, int kernel, void* stream);
+
+/* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / VATS_KERNEL_SIMT). Host only. */
+int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
+                           const int64_t q_strides[3], const int64_t k_strides[3],
+                           const int64_t v_strides[3], const int64_t o_strides[3],
+                           const void* q, const void* k, const void* v);
+
+/*
+ * KV-cache decode: one query token per sequence against its cache.
+ *
+ *   q,o       [B, H, hd]              strides (batch, head) in elements, hd contiguous
+ *   k_cache   [B, S_max, G, hd]       strides (batch, token, head) in elements
+ *   v_cache   same geometry, own strides
+ *   seq_lens  [B] int32 — tokens valid in the cache INCLUDING the token being decoded (the caller appends
+ *             the new k,v at position seq_lens[b]-1 before the call).  The query sits at position
+ *             seq_lens[b]-1 and attends keys  max(0, L-1-left) .. L-1  (left < 0 = all keys 0..L-1).
+ *             seq_lens[b] == 0 gives a zero output row.
+ *   workspace device scratch of at least vats_attn_decode_workspace_bytes(...) bytes (split-K partials).
+ */
+int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, void* o,
+                     const int32_t* seq_lens,
+                     int B, int H, int G, int hd, int S_max,
+                     const int64_t q_strides[2], const int64_t k_strides[3],
+                     const int64_t v_strides[3], const int64_t o_strides[2],
+                     float scale, int left,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left);
+
+/* Number of kernels the last successful vats_attn_decode / vats_attn_prefill on this thread launched. */
+int vats_attn_last_launch_count(void);
+
+/*
+ * Materialise the mask predicate with the kernels' own device function: out[n,i,j] = allowed(n,i,j) as 0/1.
+ * out is a DEVICE pointer to N*Tq*Tk bytes.
+ */
+int vats_attn_debug_mask(uint8_t* out, const uint8_t* q_valid, const uint8_t* k_valid,
+                         int N, int Tq, int Tk, int causal, int left, int right, void* stream);
+
+/*
+ * Host-only: the KV tile range [*first_tile, *last_tile] (inclusive, in units of `block_n` keys) that the
+ * tile-skipping logic visits for the query block [q0, q0+block_m), and whether the tiles at the two ends need the
+ * per-element predicate.  *first_tile > *last_tile means "no tile".  Pure integer arithmetic shared with the
+ * device code; lets CPU tests prove that tile skipping never drops an allowed (i,j) pair.
+ */
+int vats_attn_debug_tile_range(int q0, int block_m, int block_n, int Tq, int Tk,
+                               int causal, int left, int right,
+                               int* first_tile, int* last_tile);
+/* Host-only: 1 if tile `tile` of `block_n` keys is entirely allowed for every row of the query block (no predicate
+ * needed, k_valid aside), 0 otherwise. */
+int vats_attn_debug_tile_is_full(int tile, int q0, int block_m, int block_n, int Tq, int Tk,
+                                 int causal, int left, int right);
+
+const char* vats_attn_last_error(void);
+int vats_attn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VATS_ATTN_H_ */

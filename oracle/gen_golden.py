@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.pt by RUNNING THE UNMODIFIED REFERENCE (TEST INFRASTRUCTURE; authoring container only).
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+Each fixture holds: the reference module's constructor args and state_dict, the seeded input, the forward kwargs,
+every `F.scaled_dot_product_attention` call the module made (inputs entering the third-party call and its output),
+and the module output.  The fixtures pin the oracle (tests/test_oracle_golden.py) and, on the GPU, the drop-in
+modules and the op (tests/test_gpu_modules.py).  Reference revision: the tree mounted at /root/reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import reference as ref  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _pack_calls(calls):
+    packed = []
+    for c in calls:
+        packed.append({k: (v if not torch.is_tensor(v) else v.contiguous()) for k, v in c.items()})
+    return packed
+
+
+def llm_case(name, seed, d_model, H, G, theta, scale, B, T, left, right, causal, pad, use_qk_norm=True, fused=True):
+    m = ref.llm()
+    torch.manual_seed(seed)
+    attn = m.Attention(d_model, H, G, theta, scale, False, fused)
+    x = torch.randn(B, T, d_model)
+    padding_mask = None
+    if pad:
+        padding_mask = torch.rand(B, T) > 0.3
+        padding_mask[:, 0] = True
+    with torch.no_grad(), ref.capture_sdpa(m) as calls:
+        out, _ = attn(x, left, right, causal, padding_mask, None, None, False, False, use_qk_norm)
+    torch.save({
+        "kind": "llm", "ctor": dict(d_model=d_model, num_heads=H, query_groups=G, theta=theta, softmax_scale=scale,
+                                    use_proj_bias=False, use_qkv_proj=fused),
+        "state_dict": {k: v.clone() for k, v in attn.state_dict().items()},
+        "x": x, "kwargs": dict(left_window=left, right_window=right, causal=causal, use_qk_norm=use_qk_norm),
+        "padding_mask": padding_mask, "sdpa_calls": _pack_calls(calls), "out": out,
+    }, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), len(calls), "sdpa call(s)")
+
+
+def vit2d_case(name, seed, d_model, H, G, target, patch, B, use_qk_norm=True, windowed=False):
+    m = ref.vit2d()
+    torch.manual_seed(seed)
+    hd = d_model // H
+    attn = m.SpatialAttention(d_model, H, G, 10000.0, target, patch, 1.0 / hd ** 0.5, windowed, False, True)
+    T = (target // patch) ** 2
+    x = torch.randn(B, T, d_model)
+    with torch.no_grad(), ref.capture_sdpa(m) as calls:
+        out = attn(x, False, use_qk_norm, 4, 4)
+    torch.save({
+        "kind": "vit2d", "ctor": dict(d_model=d_model, num_heads=H, query_groups=G, rope_theta=10000.0,
+                                      target_size=target, patch_size=patch, softmax_scale=1.0 / hd ** 0.5,
+                                      use_windowed_attn=windowed, use_proj_bias=False, use_fused_proj=True),
+        "state_dict": {k: v.clone() for k, v in attn.state_dict().items()},
+        "x": x, "kwargs": dict(use_mqa=False, use_qk_norm=use_qk_norm, left_window=4, right_window=4),
+        "sdpa_calls": _pack_calls(calls), "out": out,
+    }, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), len(calls), "sdpa call(s)")
+
+
+def vit3d_case(name, seed, d_model, H, G, grid, B, pad):
+    m = ref.vit3d()
+    torch.manual_seed(seed)
+    attn = m.SpatioTemporalAttention(d_model, H, G, 10000.0, (2, 16, 16))
+    gt, gh, gw = grid
+    x = torch.randn(B, gt, gh * gw, d_model)
+    padding_mask = None
+    if pad:
+        padding_mask = torch.rand(B, gt * gh * gw) > 0.25
+        padding_mask[:, ::gt] = True  # keep at least one valid key per re-viewed row
+        padding_mask[:, : gh * gw : 1][:, 0] = True
+    with torch.no_grad(), ref.capture_sdpa(m) as calls:
+        out = attn(x, grid, False, True, (-1, -1), padding_mask)
+    torch.save({
+        "kind": "vit3d", "ctor": dict(d_model=d_model, num_heads=H, query_groups=G, rope_theta=10000.0,
+                                      patch_size=(2, 16, 16)),
+        "state_dict": {k: v.clone() for k, v in attn.state_dict().items()},
+        "x": x, "kwargs": dict(grid_size=grid, use_mqa=False, use_qk_norm=True, window_size=(-1, -1)),
+        "padding_mask": padding_mask, "sdpa_calls": _pack_calls(calls), "out": out,
+    }, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), len(calls), "sdpa call(s)")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # LLM — xsmall-like geometry (hd = 16, softmax_scale = sqrt(16) as in model_args_xsmall.py:31)
+    llm_case("llm_hd16_causal", 101, 64, 4, 2, 10000.0, 4.0, 2, 16, 128, 0, True, False)
+    llm_case("llm_hd16_causal_pad", 102, 64, 4, 2, 10000.0, 4.0, 3, 16, 128, 0, True, True)
+    llm_case("llm_hd16_noncausal_pad", 103, 64, 4, 1, 10000.0, 4.0, 2, 16, -1, -1, False, True)
+    # LLM — medium head geometry (hd = 60, H/G = 3) at a reduced width; window smaller than T (dropped by the reference)
+    llm_case("llm_hd60_causal_window", 104, 180, 3, 1, 10000.0, 60 ** -0.5, 2, 48, 8, 0, True, False)
+    llm_case("llm_hd60_nonorm_unfused", 105, 180, 3, 1, 10000.0, 60 ** -0.5, 1, 33, -1, -1, True, False,
+             use_qk_norm=False, fused=False)
+    # LLM — large head geometry (hd = 128, H/G = 4), one 128-token block + remainder
+    llm_case("llm_hd128_causal", 106, 256, 2, 1, 10000.0, 128 ** -0.5, 1, 160, 64, 0, True, True)
+    # ViT-2D — hd = 72 (medium) and hd = 48 (xsmall)
+    vit2d_case("vit2d_hd72", 201, 144, 2, 1, 64, 16, 3)
+    vit2d_case("vit2d_hd48_windowed", 202, 96, 2, 1, 96, 16, 2, windowed=True)
+    # ViT-3D — hd = 66 (large), spatial 3x3 / temporal 4, with and without key padding
+    vit3d_case("vit3d_hd66", 301, 132, 2, 1, (4, 3, 3), 2, False)
+    vit3d_case("vit3d_hd66_pad", 302, 132, 2, 1, (4, 3, 3), 2, True)
+    vit3d_case("vit3d_hd60_grid", 303, 120, 2, 2, (2, 6, 6), 1, True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+"""Thin ctypes layer over the C-ABI library ``csrc/libvats_attn.so`` (declared in ``include/vats_attn.h``).
+
+There is no fallback of any kind: if the shared library is missing or a call returns a non-zero code this module
+raises.  PyTorch is only used by the callers for device memory and streams; the signatures here are plain pointers
+and sizes.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvats_attn.so")
+
+KERNEL_AUTO = 0
+KERNEL_TCGEN05 = 1
+KERNEL_SIMT = 2
+
+# every symbol include/vats_attn.h declares (tests check that the library exports exactly these)
+EXPORTED_SYMBOLS = (
+    "vats_attn_prefill",
+    "vats_attn_prefill_ex",
+    "vats_attn_prefill_plan",
+    "vats_attn_decode",
+    "vats_attn_decode_workspace_bytes",
+    "vats_attn_last_launch_count",
+    "vats_attn_debug_mask",
+    "vats_attn_debug_tile_range",
+    "vats_attn_debug_tile_is_full",
+    "vats_attn_last_error",
+    "vats_attn_version",
+)
+
+
+class VatsAttnError(RuntimeError):
+    """A C-ABI call failed; ``code`` is the VATS_ERR_* value."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"vats_attn error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+_i64x3 = ctypes.c_int64 * 3
+_i64x2 = ctypes.c_int64 * 2
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (__graft_entry__.build()). "
+                "vats_multimodal_lm_b200 has no CPU or PyTorch fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i, f, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+        p3 = ctypes.POINTER(ctypes.c_int64)
+        lib.vats_attn_prefill.restype = i
+        lib.vats_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, vp]
+        lib.vats_attn_prefill_ex.restype = i
+        lib.vats_attn_prefill_ex.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp]
+        lib.vats_attn_prefill_plan.restype = i
+        lib.vats_attn_prefill_plan.argtypes = [i, i, i, i, i, i, p3, p3, p3, p3, vp, vp, vp]
+        lib.vats_attn_decode.restype = i
+        lib.vats_attn_decode.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, p3, p3, p3, p3, f, i, vp, sz, vp]
+        lib.vats_attn_decode_workspace_bytes.restype = sz
+        lib.vats_attn_decode_workspace_bytes.argtypes = [i, i, i, i, i, i]
+        lib.vats_attn_last_launch_count.restype = i
+        lib.vats_attn_last_launch_count.argtypes = []
+        lib.vats_attn_debug_mask.restype = i
+        lib.vats_attn_debug_mask.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
+        lib.vats_attn_debug_tile_range.restype = i
+        lib.vats_attn_debug_tile_range.argtypes = [i, i, i, i, i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
+        lib.vats_attn_debug_tile_is_full.restype = i
+        lib.vats_attn_debug_tile_is_full.argtypes = [i, i, i, i, i, i, i, i, i]
+        lib.vats_attn_last_error.restype = ctypes.c_char_p
+        lib.vats_attn_last_error.argtypes = []
+        lib.vats_attn_version.restype = i
+        lib.vats_attn_version.argtypes = []
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise VatsAttnError(rc, load().vats_attn_last_error().decode("utf-8", "replace"))
+
+
+def version() -> int:
+    return load().vats_attn_version()
+
+
+def last_launch_count() -> int:
+    return load().vats_attn_last_launch_count()
+
+
+def prefill(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int],
+            N: int, Tq: int, Tk: int, H: int, G: int, hd: int,
+            q_strides: Sequence[int], k_strides: Sequence[int], v_strides: Sequence[int], o_strides: Sequence[int],
+            scale: float, causal: bool, left: int, right: int, stream: int, kernel: int = KERNEL_AUTO) -> None:
+    lib = load()
+    _check(lib.vats_attn_prefill_ex(
+        q_ptr, k_ptr, v_ptr, o_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd,
+        _i64x3(*q_strides), _i64x3(*k_strides), _i64x3(*v_strides), _i64x3(*o_strides),
+        float(scale), int(bool(causal)), int(left), int(right), int(kernel), stream))
+
+
+def prefill_plan(N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides, o_strides,
+                 q_ptr: int, k_ptr: int, v_ptr: int) -> int:
+    return load().vats_attn_prefill_plan(N, Tq, Tk, H, G, hd, _i64x3(*q_strides), _i64x3(*k_strides),
+                                         _i64x3(*v_strides), _i64x3(*o_strides), q_ptr, k_ptr, v_ptr)
+
+
+def decode_workspace_bytes(B: int, H: int, G: int, hd: int, S_max: int, left: int) -> int:
+    return int(load().vats_attn_decode_workspace_bytes(B, H, G, hd, S_max, left))
+
+
+def decode(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, seq_lens_ptr: int, B: int, H: int, G: int, hd: int,
+           S_max: int, q_strides: Sequence[int], k_strides: Sequence[int], v_strides: Sequence[int],
+           o_strides: Sequence[int], scale: float, left: int, workspace_ptr: Optional[int], workspace_bytes: int,
+           stream: int) -> None:
+    lib = load()
+    _check(lib.vats_attn_decode(
+        q_ptr, k_ptr, v_ptr, o_ptr, seq_lens_ptr, B, H, G, hd, S_max,
+        _i64x2(*q_strides), _i64x3(*k_strides), _i64x3(*v_strides), _i64x2(*o_strides),
+        float(scale), int(left), workspace_ptr, workspace_bytes, stream))
+
+
+def debug_mask(out_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int], N: int, Tq: int, Tk: int,
+               causal: bool, left: int, right: int, stream: int) -> None:
+    _check(load().vats_attn_debug_mask(out_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, int(bool(causal)), int(left),
+                                       int(right), stream))
+
+
+def debug_tile_range(q0: int, block_m: int, block_n: int, Tq: int, Tk: int, causal: bool, left: int, right: int):
+    first, last = ctypes.c_int(0), ctypes.c_int(0)
+    _check(load().vats_attn_debug_tile_range(q0, block_m, block_n, Tq, Tk, int(bool(causal)), int(left), int(right),
+                                             ctypes.byref(first), ctypes.byref(last)))
+    return first.value, last.value
+
+
+def debug_tile_is_full(tile: int, q0: int, block_m: int, block_n: int, Tq: int, Tk: int, causal: bool, left: int,
+                       right: int) -> bool:
+    return bool(load().vats_attn_debug_tile_is_full(tile, q0, block_m, block_n, Tq, Tk, int(bool(causal)), int(left),
+                                                    int(right)))

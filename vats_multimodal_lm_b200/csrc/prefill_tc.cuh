@@ -1,0 +1,411 @@
+// prefill_tc.cuh — GQA + sliding-window attention on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces the attention core of the reference: the SDPA call and mask build of
+// src/optimized_attention.py:657-723 (LLM), vit_2d/optimized_attention.py:348-423 and
+// vit_3d/optimized_attention.py:185-348, with the window semantics of the (dead) FA2 call at
+// src/optimized_attention.py:628-635, and `extend_kv_heads` (utils/attention_utils.py:7-27) folded into indexing.
+//
+// One CTA owns one KV group g of one sequence n, one block of 128 query tokens, and a PAIR of query heads of that
+// group (M-tile 0 and M-tile 1, 128 rows each).  Both tiles consume the same K/V tiles from shared memory
+// (GQA head-group reuse) and ping-pong on the tensor core so the softmax of one overlaps the MMAs of the other.
+//
+//   warps 0-3   softmax warpgroup of tile 0: thread r owns S row r (TMEM lane r) — row max / row sum are in-thread
+//   warps 4-7   softmax warpgroup of tile 1
+//   warp  8     TMA producer: Q tiles once, then K_j, V_j into mbarrier-guarded rings (128B-swizzled boxes)
+//   warp  9     MMA issuer (one elected lane): S = Q·K^T (SS, both K-major), O += P·V (TS: P from TMEM, V MN-major)
+//
+//   TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (bf16) aliases the first 64 columns of S.
+//
+// KV tiles outside the (causal, window) band of the query block are skipped entirely (mask.cuh: tile_range); only
+// tiles cut by the band, by the end of the sequence or by k_valid run the per-element predicate.
+// Softmax is online with lazy rescaling: O is rescaled only when the running maximum grows by more than 2^8.
+#pragma once
+#include "mask.cuh"
+#include "prefill_simt.cuh"  // PrefillParams
+#include "ptx.cuh"
+
+namespace vats {
+
+constexpr int kTcBlockM = 128;
+constexpr int kTcBlockN = 128;
+constexpr int kTcThreads = 320;
+constexpr int kTcRegionBytes = 128 * 128;  // 128 rows x 64 bf16, one 128B-swizzled box
+constexpr int kTcMaxStages = 4;
+constexpr float kTcRescaleThreshold = 8.0f;  // log2 units
+
+struct TcParams {
+  PrefillParams a;
+  int hd_pad;        // head dim rounded up to a multiple of 16 (MMA K of QK^T, MMA N of PV)
+  int regions;       // ceil(hd_pad / 64) swizzle regions per tile
+  int q_blocks;      // ceil(Tq / 128)
+  int pairs;         // ceil(hpg / 2) head pairs per KV group
+  int nk, nv;        // ring depths
+  int merged_q, merged_kv;  // 1: tensor map inner dim is heads*hd and the head is selected by the inner coordinate
+  int q_fixup;       // 1: zero the Q columns [hd, hd_pad) in smem (merged map fetched neighbour-head data there)
+  int o_vec16;       // 1: O rows may be written with 16-byte stores
+};
+
+struct TcSmemBarriers {
+  uint64_t q_full[2];
+  uint64_t q_fixed[2];
+  uint64_t k_full[kTcMaxStages], k_empty[kTcMaxStages];
+  uint64_t v_full[kTcMaxStages], v_empty[kTcMaxStages];
+  uint64_t s_full[2];
+  uint64_t p_full[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(int regions, int nk, int nv) {
+  return (size_t)(2 + nk + nv) * regions * kTcRegionBytes + 1024 /*alignment slack*/ + sizeof(TcSmemBarriers);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
+                  const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v) {
+  using namespace ptx;
+  extern __shared__ unsigned char smem_raw[];
+  const PrefillParams& a = P.a;
+
+  // ---- carve shared memory (1024-byte aligned for the 128B swizzle atoms)
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t tile_bytes = (uint32_t)P.regions * kTcRegionBytes;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + 2 * tile_bytes;
+  const uint32_t sV = sK + (uint32_t)P.nk * tile_bytes;
+  TcSmemBarriers* bars =
+      reinterpret_cast<TcSmemBarriers*>(smem_raw + (base - raw) + (size_t)(2 + P.nk + P.nv) * tile_bytes);
+
+  // ---- work decode: q block fastest, then (group, pair), then sequence
+  int bid = blockIdx.x;
+  const int qb = (P.q_blocks - 1) - (bid % P.q_blocks);  // heavy (late) causal blocks first
+  bid /= P.q_blocks;
+  const int pair = bid % P.pairs;
+  bid /= P.pairs;
+  const int g = bid % a.G;
+  const int n = bid / a.G;
+  const int q0 = qb * kTcBlockM;
+  const int hh0 = pair * 2;  // head-in-group of tile 0
+  const bool active1 = (hh0 + 1) < a.hpg;
+  const int head0 = g * a.hpg + hh0;
+
+  int t_first, t_last;
+  tile_range(a.mask, q0, kTcBlockM, kTcBlockN, &t_first, &t_last);
+  const int n_tiles = t_last - t_first + 1;  // <= 0: nothing to attend
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bars->q_full[t]), 1);
+      mbar_init(smem_u32(&bars->q_fixed[t]), 128);
+      mbar_init(smem_u32(&bars->s_full[t]), 1);
+      mbar_init(smem_u32(&bars->p_full[t]), 128);
+    }
+    for (int s = 0; s < kTcMaxStages; ++s) {
+      mbar_init(smem_u32(&bars->k_full[s]), 1);
+      mbar_init(smem_u32(&bars->k_empty[s]), 1);
+      mbar_init(smem_u32(&bars->v_full[s]), 1);
+      mbar_init(smem_u32(&bars->v_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->o_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 8) {
+    // =========================================================== TMA producer
+    if (lane == 0 && n_tiles > 0) {
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !active1) break;
+        const uint32_t bar = smem_u32(&bars->q_full[t]);
+        mbar_expect_tx(bar, tile_bytes);
+        const int h = head0 + t;
+        for (int c = 0; c < P.regions; ++c) {
+          const int c0 = P.merged_q ? h * a.hd + 64 * c : 64 * c;
+          const int c1 = P.merged_q ? 0 : h;
+          tma_load_4d(sQ + t * tile_bytes + c * kTcRegionBytes, &tmap_q, bar, c0, c1, q0, n);
+        }
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int k0 = (t_first + j) * kTcBlockN;
+        {
+          const int s = j % P.nk;
+          const uint32_t ph = (uint32_t)(j / P.nk) & 1u;
+          mbar_wait(smem_u32(&bars->k_empty[s]), ph ^ 1u);
+          const uint32_t bar = smem_u32(&bars->k_full[s]);
+          mbar_expect_tx(bar, tile_bytes);
+          for (int c = 0; c < P.regions; ++c) {
+            const int c0 = P.merged_kv ? g * a.hd + 64 * c : 64 * c;
+            const int c1 = P.merged_kv ? 0 : g;
+            tma_load_4d(sK + s * tile_bytes + c * kTcRegionBytes, &tmap_k, bar, c0, c1, k0, n);
+          }
+        }
+        {
+          const int s = j % P.nv;
+          const uint32_t ph = (uint32_t)(j / P.nv) & 1u;
+          mbar_wait(smem_u32(&bars->v_empty[s]), ph ^ 1u);
+          const uint32_t bar = smem_u32(&bars->v_full[s]);
+          mbar_expect_tx(bar, tile_bytes);
+          for (int c = 0; c < P.regions; ++c) {
+            const int c0 = P.merged_kv ? g * a.hd + 64 * c : 64 * c;
+            const int c1 = P.merged_kv ? 0 : g;
+            tma_load_4d(sV + s * tile_bytes + c * kTcRegionBytes, &tmap_v, bar, c0, c1, k0, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================================== MMA issuer
+    if (lane == 0 && n_tiles > 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kTcBlockM, kTcBlockN, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(kTcBlockM, P.hd_pad, 0, 1);
+      const int ksteps = P.hd_pad / 16;
+      const int ntile_heads = active1 ? 2 : 1;
+
+      auto issue_s = [&](int t, int kstage) {
+        const uint32_t qa = sQ + t * tile_bytes;
+        const uint32_t kb = sK + kstage * tile_bytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t o = (uint32_t)(ks >> 2) * kTcRegionBytes + (uint32_t)(ks & 3) * 32u;
+          mma_ss(tmem + t * 128, make_smem_desc_sw128(qa + o, 16, 1024), make_smem_desc_sw128(kb + o, 16, 1024),
+                 idesc_s, ks > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int vstage, bool accumulate) {
+        const uint32_t vb = sV + vstage * tile_bytes;
+        for (int ks = 0; ks < kTcBlockN / 16; ++ks) {
+          mma_ts(tmem + 256 + t * 128, tmem + t * 128 + ks * 8,
+                 make_smem_desc_sw128(vb + ks * 2048, kTcRegionBytes, 1024), idesc_o,
+                 (accumulate || ks > 0) ? 1u : 0u);
+        }
+      };
+
+      for (int t = 0; t < ntile_heads; ++t) {
+        mbar_wait(smem_u32(&bars->q_full[t]), 0);
+        if (P.q_fixup) mbar_wait(smem_u32(&bars->q_fixed[t]), 0);
+      }
+      mbar_wait(smem_u32(&bars->k_full[0]), 0);
+      tc_fence_after();
+      for (int t = 0; t < ntile_heads; ++t) {
+        issue_s(t, 0);
+        tc_commit(smem_u32(&bars->s_full[t]));
+      }
+      tc_commit(smem_u32(&bars->k_empty[0]));
+
+      for (int j = 0; j < n_tiles; ++j) {
+        const int vs = j % P.nv;
+        const bool has_next = (j + 1) < n_tiles;
+        const int ksn = (j + 1) % P.nk;
+        mbar_wait(smem_u32(&bars->v_full[vs]), (uint32_t)(j / P.nv) & 1u);
+        for (int t = 0; t < ntile_heads; ++t) {
+          mbar_wait(smem_u32(&bars->p_full[t]), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_pv(t, vs, j > 0);
+          if (has_next) {
+            if (t == 0) {
+              mbar_wait(smem_u32(&bars->k_full[ksn]), (uint32_t)((j + 1) / P.nk) & 1u);
+              tc_fence_after();
+            }
+            issue_s(t, ksn);
+            tc_commit(smem_u32(&bars->s_full[t]));
+          }
+        }
+        tc_commit(smem_u32(&bars->v_empty[vs]));
+        if (has_next) tc_commit(smem_u32(&bars->k_empty[ksn]));
+      }
+      tc_commit(smem_u32(&bars->o_full));
+    }
+  } else {
+    // =========================================================== softmax warpgroups (tile t = warp / 4)
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;           // row within the tile == TMEM lane
+    const int tok = q0 + r;
+    const int head = head0 + t;
+    const bool tile_active = (t == 0) || active1;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_base + (uint32_t)t * 128;
+    const uint32_t tO = tmem + lane_base + 256 + (uint32_t)t * 128;
+
+    float l_run = 0.f;
+    float m_used = -INFINITY;  // reference maximum in scaled-log2 units; -inf = not set yet
+
+    if (tile_active && n_tiles > 0) {
+      if (P.q_fixup) {
+        mbar_wait(smem_u32(&bars->q_full[t]), 0);
+        unsigned char* qrow = smem_raw + (sQ - raw) + t * tile_bytes;
+        for (int c = a.hd; c < P.hd_pad; ++c) {
+          const int cw = c & 63;
+          const uint32_t off = (uint32_t)(c >> 6) * kTcRegionBytes + (uint32_t)r * 128u +
+                               ((((uint32_t)cw * 2u) >> 4) ^ ((uint32_t)r & 7u)) * 16u + (((uint32_t)cw * 2u) & 15u);
+          *reinterpret_cast<uint16_t*>(qrow + off) = 0;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&bars->q_fixed[t]));
+      }
+
+      for (int j = 0; j < n_tiles; ++j) {
+        const int tile = t_first + j;
+        const int k0 = tile * kTcBlockN;
+        mbar_wait(smem_u32(&bars->s_full[t]), (uint32_t)j & 1u);
+        tc_fence_after();
+        uint32_t sr[128];
+        tmem_ld_32x32b_x32(tS + 0, sr + 0);
+        tmem_ld_32x32b_x32(tS + 32, sr + 32);
+        tmem_ld_32x32b_x32(tS + 64, sr + 64);
+        tmem_ld_32x32b_x32(tS + 96, sr + 96);
+        tmem_ld_wait();
+
+        // ---- predicate (edge tiles only)
+        const bool full = tile_is_full(a.mask, tile, q0, kTcBlockM, kTcBlockN);
+        if (!full || a.k_valid != nullptr) {
+          uint32_t kbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          if (a.k_valid != nullptr) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int key = k0 + w * 32 + lane;
+              const bool ok = key < a.Tk && a.k_valid[(long long)n * a.Tk + key] != 0;
+              kbits[w] = __ballot_sync(0xffffffffu, ok);
+            }
+          }
+          long long lo = key_lo(a.mask, tok) - k0;
+          long long hi = key_hi(a.mask, tok) - k0;
+          const int lo_c = lo < 0 ? 0 : (lo > 128 ? 128 : (int)lo);
+          const int hi_c = hi < -1 ? -1 : (hi > 127 ? 127 : (int)hi);
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            const bool ok = (c >= lo_c) && (c <= hi_c) && ((kbits[c >> 5] >> (c & 31)) & 1u);
+            if (!ok) sr[c] = 0xff800000u;  // -inf
+          }
+        }
+
+        // ---- row max of this tile (raw logits), in-thread
+        float mt0 = __uint_as_float(sr[0]), mt1 = __uint_as_float(sr[1]), mt2 = __uint_as_float(sr[2]),
+              mt3 = __uint_as_float(sr[3]);
+#pragma unroll
+        for (int c = 4; c < 128; c += 4) {
+          mt0 = fmaxf(mt0, __uint_as_float(sr[c]));
+          mt1 = fmaxf(mt1, __uint_as_float(sr[c + 1]));
+          mt2 = fmaxf(mt2, __uint_as_float(sr[c + 2]));
+          mt3 = fmaxf(mt3, __uint_as_float(sr[c + 3]));
+        }
+        const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3)) * a.scale_log2;  // scaled-log2 units (scale > 0)
+
+        // ---- lazy rescale of the running state
+        float factor = 1.f;
+        if (m_used == -INFINITY) {
+          m_used = mt;  // may stay -inf; O and l are still zero, nothing to rescale
+        } else if (mt > m_used + kTcRescaleThreshold) {
+          factor = ex2(m_used - mt);
+          m_used = mt;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, factor != 1.f)) {
+          l_run *= factor;
+          for (int c = 0; c < P.hd_pad; c += 16) {
+            uint32_t orr[16];
+            tmem_ld_32x32b_x16(tO + c, orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+            tmem_st_32x32b_x16(tO + c, orr);
+          }
+        }
+
+        // ---- p = exp2(s*scale_log2 - m_used), row sum, pack to bf16, write P over S
+        const float mref = (m_used == -INFINITY) ? 0.f : m_used;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[64];
+#pragma unroll
+        for (int c = 0; c < 128; c += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sr[c]), a.scale_log2, -mref));
+          const float p1 = ex2(fmaf(__uint_as_float(sr[c + 1]), a.scale_log2, -mref));
+          sum0 += p0;
+          sum1 += p1;
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+        }
+        l_run += sum0 + sum1;
+        tmem_st_32x32b_x32(tS + 0, pk + 0);
+        tmem_st_32x32b_x32(tS + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->p_full[t]));
+      }
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global
+    // (tcgen05.ld is warp-collective: every lane of an active tile's warps runs the loads; only the global
+    //  stores are predicated on the row being inside the sequence)
+    if (tile_active) {
+      const bool do_store = tok < a.Tq;
+      bool qok = true;
+      if (do_store && a.q_valid != nullptr) qok = a.q_valid[(long long)n * a.Tq + tok] != 0;
+      const float inv = (qok && l_run > 0.f && n_tiles > 0) ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = a.o + n * a.os_n + (long long)tok * a.os_t + (long long)head * a.os_h;
+      if (n_tiles > 0) {
+        mbar_wait(smem_u32(&bars->o_full), 0);
+        tc_fence_after();
+      }
+      for (int c = 0; c < P.hd_pad; c += 16) {
+        uint32_t orr[16];
+        if (n_tiles > 0) {
+          tmem_ld_32x32b_x16(tO + c, orr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) orr[i] = 0u;
+        }
+        __syncwarp();
+        if (do_store) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          w[i] = pack_bf16x2(__uint_as_float(orr[2 * i]) * inv, __uint_as_float(orr[2 * i + 1]) * inv);
+        if (P.o_vec16 && c + 16 <= a.hd) {
+          *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = c + 2 * i;
+            if (e + 1 < a.hd) {
+              if ((reinterpret_cast<uintptr_t>(orow + e) & 3u) == 0) {
+                *reinterpret_cast<uint32_t*>(orow + e) = w[i];
+              } else {
+                reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(w[i] & 0xffffu);
+                reinterpret_cast<uint16_t*>(orow)[e + 1] = (uint16_t)(w[i] >> 16);
+              }
+            } else if (e < a.hd) {
+              reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(w[i] & 0xffffu);
+            }
+          }
+        }
+        }  // do_store
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace vats

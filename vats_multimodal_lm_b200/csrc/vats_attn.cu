@@ -1,0 +1,525 @@
+// vats_attn.cu — C-ABI entry points (include/vats_attn.h): validation, kernel choice, TMA descriptors, launches.
+//
+// No CPU fallback and no second backend: every path below ends in one of the three sm_100a kernels
+// (prefill_tc_kernel, prefill_simt_kernel, decode_split_kernel [+ decode_combine_kernel]) or in an error.
+#include "../../include/vats_attn.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+
+#include "decode.cuh"
+#include "mask.cuh"
+#include "prefill_simt.cuh"
+#include "prefill_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(VATS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- device gate: sm_100 only
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return fail(VATS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_ok = 0;
+  if (cached_dev == dev) return cached_ok ? VATS_OK : fail(VATS_ERR_UNSUPPORTED, "device %d is not sm_100", dev);
+  int major = 0, minor = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  cached_dev = dev;
+  cached_ok = (major == 10);
+  if (!cached_ok)
+    return fail(VATS_ERR_UNSUPPORTED, "device %d is sm_%d%d; the kernels are built for sm_100a only", dev, major, minor);
+  return VATS_OK;
+}
+
+// ---- cuTensorMapEncodeTiled through the runtime (libcuda is not linked at build time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// A [N, T, heads, hd] bf16 tensor (strides in elements, hd contiguous) as a 4-D tiled map with a
+// (64 x 1 x 128 x 1) box, 128-byte swizzle.
+//   split  mode: dims (hd, heads, T, N)          — needs the head stride to be a multiple of 8 elements
+//   merged mode: dims (heads*hd, 1, T, N)        — heads contiguous (stride == hd); the head is picked by the inner
+//                                                   coordinate, which lets head dims like 60 or 66 through TMA
+struct MapPlan {
+  bool ok;
+  bool merged;
+};
+
+MapPlan plan_map(const void* ptr, int heads, int hd, const int64_t s[3]) {
+  MapPlan r{false, false};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return r;
+  if (s[0] % 8 != 0 || s[1] % 8 != 0) return r;
+  if (s[2] % 8 == 0) {
+    r.ok = true;
+    r.merged = false;
+    return r;
+  }
+  if (s[2] == hd || heads == 1) {
+    r.ok = true;
+    r.merged = true;
+    return r;
+  }
+  return r;
+}
+
+int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3], bool merged) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  if (merged) {
+    dims[0] = (cuuint64_t)heads * hd;
+    dims[1] = 1;
+    strides[0] = (cuuint64_t)(s[1] > 0 ? s[1] : (int64_t)heads * hd) * 2;  // unused (dim 1 has extent 1)
+  } else {
+    dims[0] = (cuuint64_t)hd;
+    dims[1] = (cuuint64_t)heads;
+    strides[0] = (cuuint64_t)s[2] * 2;
+  }
+  dims[2] = (cuuint64_t)T;
+  dims[3] = (cuuint64_t)N;
+  strides[1] = (cuuint64_t)s[1] * 2;
+  strides[2] = (cuuint64_t)s[0] * 2;
+  // extent-1 dimensions may carry a zero stride in PyTorch; give TMA something legal
+  if (T == 1 || strides[1] == 0) strides[1] = (cuuint64_t)heads * hd * 2;
+  if (N == 1 || strides[2] == 0) strides[2] = strides[1] * (cuuint64_t)T;
+  if (strides[0] == 0) strides[0] = (cuuint64_t)hd * 2;
+  const cuuint32_t box[4] = {64, 1, 128, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+    return fail(VATS_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (CUresult %d) dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu)",
+                (int)rc, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+                (unsigned long long)strides[2]);
+  return VATS_OK;
+}
+
+struct PrefillArgs {
+  const void *q, *k, *v;
+  void* o;
+  const uint8_t *q_valid, *k_valid;
+  int N, Tq, Tk, H, G, hd;
+  const int64_t *qs, *ks, *vs, *os;
+  float scale;
+  int causal, left, right;
+};
+
+int validate_prefill(const PrefillArgs& A) {
+  if (A.N < 0 || A.Tq < 0 || A.Tk < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
+  if (A.H <= 0 || A.G <= 0 || A.hd <= 0) return fail(VATS_ERR_INVALID_ARGUMENT, "H, G, hd must be positive");
+  if (A.H % A.G != 0)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "num_heads (%d) must be divisible by query_groups (%d)", A.H, A.G);
+  if (!(A.scale > 0.f) || !std::isfinite(A.scale))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "scale must be a positive finite float (got %g)", (double)A.scale);
+  if (!A.qs || !A.ks || !A.vs || !A.os) return fail(VATS_ERR_INVALID_ARGUMENT, "stride arrays must not be NULL");
+  if (A.N > 0 && A.Tq > 0 && (!A.q || !A.o)) return fail(VATS_ERR_INVALID_ARGUMENT, "q / o must not be NULL");
+  if (A.N > 0 && A.Tk > 0 && (!A.k || !A.v)) return fail(VATS_ERR_INVALID_ARGUMENT, "k / v must not be NULL");
+  return VATS_OK;
+}
+
+bool tc_legal(const PrefillArgs& A, MapPlan* pq, MapPlan* pk, MapPlan* pv) {
+  if (A.hd > 128 || A.Tk <= 0) return false;
+  *pq = plan_map(A.q, A.H, A.hd, A.qs);
+  *pk = plan_map(A.k, A.G, A.hd, A.ks);
+  *pv = plan_map(A.v, A.G, A.hd, A.vs);
+  if (!pq->ok || !pk->ok || !pv->ok) return false;
+  // TMA coordinates are int32
+  if ((long long)A.H * A.hd > 0x7fffffffLL) return false;
+  return true;
+}
+
+void fill_common(vats::PrefillParams& p, const PrefillArgs& A) {
+  p.q = reinterpret_cast<const __nv_bfloat16*>(A.q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(A.k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(A.v);
+  p.o = reinterpret_cast<__nv_bfloat16*>(A.o);
+  p.q_valid = A.q_valid;
+  p.k_valid = A.k_valid;
+  p.N = A.N; p.Tq = A.Tq; p.Tk = A.Tk; p.H = A.H; p.G = A.G; p.hd = A.hd;
+  p.hpg = A.H / A.G;
+  p.qs_n = A.qs[0]; p.qs_t = A.qs[1]; p.qs_h = A.qs[2];
+  p.ks_n = A.ks[0]; p.ks_t = A.ks[1]; p.ks_h = A.ks[2];
+  p.vs_n = A.vs[0]; p.vs_t = A.vs[1]; p.vs_h = A.vs[2];
+  p.os_n = A.os[0]; p.os_t = A.os[1]; p.os_h = A.os[2];
+  p.scale_log2 = A.scale * 1.4426950408889634f;
+  p.mask.Tq = A.Tq; p.mask.Tk = A.Tk;
+  p.mask.causal = A.causal ? 1 : 0;
+  p.mask.left = A.left; p.mask.right = A.right;
+}
+
+int launch_simt(const PrefillArgs& A, cudaStream_t st) {
+  if (A.hd > vats::kSimtMaxHd) return fail(VATS_ERR_UNSUPPORTED, "head_dim %d > %d is not supported", A.hd, vats::kSimtMaxHd);
+  vats::PrefillParams p;
+  fill_common(p, A);
+  const int total_rows = A.Tq * p.hpg;
+  const int rb = (total_rows + vats::kSimtRows - 1) / vats::kSimtRows;
+  if (A.G > 65535 || A.N > 65535)
+    return fail(VATS_ERR_UNSUPPORTED, "SIMT kernel grid limit: G and N must be <= 65535 (got G=%d N=%d)", A.G, A.N);
+  dim3 grid(rb, A.G, A.N);
+  const size_t smem = (size_t)(2 * vats::kSimtTileN + vats::kSimtRows) * (A.hd + 1) * sizeof(float);
+  const int cpln = (A.hd + 31) / 32;
+#define VATS_SIMT_CASE(C)                                                                                         \
+  case C: {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(vats::prefill_simt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                                                    \
+    vats::prefill_simt_kernel<C><<<grid, vats::kSimtWarps * 32, smem, st>>>(p);                                   \
+  } break;
+  switch (cpln) {
+    VATS_SIMT_CASE(1)
+    VATS_SIMT_CASE(2)
+    VATS_SIMT_CASE(3)
+    VATS_SIMT_CASE(4)
+    VATS_SIMT_CASE(5)
+    VATS_SIMT_CASE(6)
+    VATS_SIMT_CASE(7)
+    VATS_SIMT_CASE(8)
+    default:
+      return fail(VATS_ERR_UNSUPPORTED, "head_dim %d not supported by the SIMT kernel", A.hd);
+  }
+#undef VATS_SIMT_CASE
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return VATS_OK;
+}
+
+int launch_tc(const PrefillArgs& A, const MapPlan& pq, const MapPlan& pk, const MapPlan& pv, cudaStream_t st) {
+  vats::TcParams P;
+  std::memset(&P, 0, sizeof(P));
+  fill_common(P.a, A);
+  P.hd_pad = (A.hd + 15) / 16 * 16;
+  P.regions = (P.hd_pad + 63) / 64;
+  P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
+  P.pairs = (P.a.hpg + 1) / 2;
+  P.merged_q = pq.merged ? 1 : 0;
+  P.merged_kv = pk.merged ? 1 : 0;
+  if (pk.merged != pv.merged) return fail(VATS_ERR_UNSUPPORTED, "k and v must share the same head layout class");
+  // A merged map fetches the neighbouring head's first elements into the padding columns; a split map zero-fills them.
+  P.q_fixup = (pq.merged && P.hd_pad != A.hd) ? 1 : 0;
+  P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
+               A.os[2] % 8 == 0 && A.hd % 8 == 0)
+                  ? 1
+                  : 0;
+  // ring depths: fill the 227 KB of shared memory (also pins one CTA per SM, which owns all 512 TMEM columns)
+  const int tile_bytes = P.regions * vats::kTcRegionBytes;
+  int stages = (int)((227 * 1024 - 1024 - (int)sizeof(vats::TcSmemBarriers) - 2 * tile_bytes) / tile_bytes);
+  int nk = stages / 2, nv = stages - nk;
+  if (nk > vats::kTcMaxStages) nk = vats::kTcMaxStages;
+  if (nv > vats::kTcMaxStages) nv = vats::kTcMaxStages;
+  if (nk < 1 || nv < 1) return fail(VATS_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  P.nk = nk;
+  P.nv = nv;
+  const size_t smem = vats::tc_smem_bytes(P.regions, nk, nv);
+
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs, pq.merged)) != VATS_OK) return rc;
+  if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks, pk.merged)) != VATS_OK) return rc;
+  if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs, pv.merged)) != VATS_OK) return rc;
+
+  const long long ctas = (long long)A.N * A.G * P.pairs * P.q_blocks;
+  if (ctas > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "grid too large");
+  static thread_local size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  vats::prefill_tc_kernel<<<(unsigned)ctas, vats::kTcThreads, smem, st>>>(P, mq, mk, mv);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return VATS_OK;
+}
+
+int choose_kernel(const PrefillArgs& A, MapPlan* pq, MapPlan* pk, MapPlan* pv) {
+  const bool legal = tc_legal(A, pq, pk, pv);
+  if (!legal) return VATS_KERNEL_SIMT;
+  // Tiles are 128 x 128: below 32 keys or 32 query tokens more than 3/4 of every MMA would be padding and the
+  // problem is bandwidth-bound anyway (ViT-3D temporal pass: 8 tokens per sequence).
+  if (A.Tk < 32 || A.Tq < 16) return VATS_KERNEL_SIMT;
+  return VATS_KERNEL_TCGEN05;
+}
+
+int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
+  g_launches = 0;
+  int rc = validate_prefill(A);
+  if (rc != VATS_OK) return rc;
+  if ((rc = check_device()) != VATS_OK) return rc;
+  if (A.N == 0 || A.Tq == 0) return VATS_OK;  // empty output (reference: T == 0 returns an empty tensor, :405-407)
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MapPlan pq{false, false}, pk{false, false}, pv{false, false};
+  int auto_choice = choose_kernel(A, &pq, &pk, &pv);
+  if (kernel == VATS_KERNEL_AUTO) kernel = auto_choice;
+  if (kernel == VATS_KERNEL_TCGEN05) {
+    if (!tc_legal(A, &pq, &pk, &pv))
+      return fail(VATS_ERR_UNSUPPORTED,
+                  "geometry is not TMA-legal for the tcgen05 kernel (hd=%d, need hd<=128, 16-byte aligned base and "
+                  "token/sequence strides, heads contiguous or head stride %% 8 == 0)",
+                  A.hd);
+    return launch_tc(A, pq, pk, pv, st);
+  }
+  if (kernel == VATS_KERNEL_SIMT) return launch_simt(A, st);
+  return fail(VATS_ERR_INVALID_ARGUMENT, "unknown kernel selector %d", kernel);
+}
+
+__global__ void debug_mask_kernel(uint8_t* out, const uint8_t* q_valid, const uint8_t* k_valid, int N, int Tq, int Tk,
+                                  vats::MaskParams mp) {
+  const long long total = (long long)N * Tq * Tk;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Tk);
+    const int i = (int)((idx / Tk) % Tq);
+    const int n = (int)(idx / ((long long)Tk * Tq));
+    bool ok = vats::allowed_geom(mp, i, j);
+    if (ok && q_valid) ok = q_valid[(long long)n * Tq + i] != 0;
+    if (ok && k_valid) ok = k_valid[(long long)n * Tk + j] != 0;
+    out[idx] = ok ? 1 : 0;
+  }
+}
+
+template <int VEC, int LPK, int CPL>
+int launch_decode_hpg(const vats::DecodeParams& p, int hpg_tile, dim3 grid, size_t smem, cudaStream_t st) {
+  constexpr int U = 8;
+  switch (hpg_tile) {
+    case 1: vats::decode_split_kernel<VEC, LPK, CPL, 1, U><<<grid, vats::kDecodeThreads, smem, st>>>(p); break;
+    case 2: vats::decode_split_kernel<VEC, LPK, CPL, 2, U><<<grid, vats::kDecodeThreads, smem, st>>>(p); break;
+    case 3: vats::decode_split_kernel<VEC, LPK, CPL, 3, U><<<grid, vats::kDecodeThreads, smem, st>>>(p); break;
+    case 4: vats::decode_split_kernel<VEC, LPK, CPL, 4, U><<<grid, vats::kDecodeThreads, smem, st>>>(p); break;
+    default: return fail(VATS_ERR_UNSUPPORTED, "internal: bad head tile %d", hpg_tile);
+  }
+  return VATS_OK;
+}
+
+int decode_chunk_and_splits(int S_max, int left, int* chunk, int* splits) {
+  long long window = S_max;
+  if (left >= 0 && (long long)left + 1 < window) window = (long long)left + 1;
+  if (window < 1) window = 1;
+  int ch = 256;
+  *chunk = ch;
+  *splits = (int)((window + ch - 1) / ch);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vats_attn_version(void) { return VATS_ATTN_VERSION; }
+const char* vats_attn_last_error(void) { return g_err; }
+int vats_attn_last_launch_count(void) { return g_launches; }
+
+int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o, const uint8_t* q_valid,
+                         const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
+                         const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                         const int64_t o_strides[3], float scale, int causal, int left, int right, int kernel,
+                         void* stream) {
+  PrefillArgs A{q, k, v, o, q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
+                scale, causal, left, right};
+  return prefill_impl(A, kernel, stream);
+}
+
+int vats_attn_prefill(const void* q, const void* k, const void* v, void* o, const uint8_t* q_valid,
+                      const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
+                      const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                      const int64_t o_strides[3], float scale, int causal, int left, int right, void* stream) {
+  return vats_attn_prefill_ex(q, k, v, o, q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides,
+                              o_strides, scale, causal, left, right, VATS_KERNEL_AUTO, stream);
+}
+
+int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd, const int64_t q_strides[3],
+                           const int64_t k_strides[3], const int64_t v_strides[3], const int64_t o_strides[3],
+                           const void* q, const void* k, const void* v) {
+  PrefillArgs A{q, k, v, nullptr, nullptr, nullptr, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
+                1.f, 0, -1, -1};
+  if (H <= 0 || G <= 0 || hd <= 0 || H % G != 0 || !q_strides || !k_strides || !v_strides) return -1;
+  MapPlan pq, pk, pv;
+  return choose_kernel(A, &pq, &pk, &pv);
+}
+
+size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left) {
+  (void)G;
+  if (B <= 0 || H <= 0 || hd <= 0 || S_max <= 0) return 0;
+  int chunk, splits;
+  decode_chunk_and_splits(S_max, left, &chunk, &splits);
+  if (splits <= 1) return 16;
+  return (size_t)B * H * splits * ((size_t)hd + 2) * sizeof(float);
+}
+
+int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, void* o, const int32_t* seq_lens,
+                     int B, int H, int G, int hd, int S_max, const int64_t q_strides[2], const int64_t k_strides[3],
+                     const int64_t v_strides[3], const int64_t o_strides[2], float scale, int left, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (B < 0 || S_max < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
+  if (H <= 0 || G <= 0 || hd <= 0) return fail(VATS_ERR_INVALID_ARGUMENT, "H, G, hd must be positive");
+  if (H % G != 0)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "num_heads (%d) must be divisible by query_groups (%d)", H, G);
+  if (!(scale > 0.f) || !std::isfinite(scale))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "scale must be a positive finite float (got %g)", (double)scale);
+  if (!q_strides || !k_strides || !v_strides || !o_strides)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "stride arrays must not be NULL");
+  int rc = check_device();
+  if (rc != VATS_OK) return rc;
+  if (B == 0) return VATS_OK;
+  if (!q || !o || !seq_lens) return fail(VATS_ERR_INVALID_ARGUMENT, "q / o / seq_lens must not be NULL");
+  if (S_max > 0 && (!k_cache || !v_cache)) return fail(VATS_ERR_INVALID_ARGUMENT, "k_cache / v_cache must not be NULL");
+  if (hd > 256) return fail(VATS_ERR_UNSUPPORTED, "decode supports head_dim <= 256 (got %d)", hd);
+  if (hd % 2 != 0) return fail(VATS_ERR_UNSUPPORTED, "decode needs an even head_dim (got %d)", hd);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  vats::DecodeParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(k_cache);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(v_cache);
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.seq_lens = seq_lens;
+  p.B = B; p.H = H; p.G = G; p.hd = hd; p.S_max = S_max;
+  p.hpg = H / G;
+  p.qs_b = q_strides[0]; p.qs_h = q_strides[1];
+  p.ks_b = k_strides[0]; p.ks_t = k_strides[1]; p.ks_h = k_strides[2];
+  p.vs_b = v_strides[0]; p.vs_t = v_strides[1]; p.vs_h = v_strides[2];
+  p.os_b = o_strides[0]; p.os_h = o_strides[1];
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.left = left;
+  decode_chunk_and_splits(S_max > 0 ? S_max : 1, left, &p.chunk, &p.num_splits);
+  if (p.num_splits > 1) {
+    const size_t need = vats_attn_decode_workspace_bytes(B, H, G, hd, S_max, left);
+    if (!workspace || workspace_bytes < need)
+      return fail(VATS_ERR_WORKSPACE, "decode workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    p.ws_acc = reinterpret_cast<float*>(workspace);
+    p.ws_ml = p.ws_acc + (size_t)B * H * p.num_splits * hd;
+  }
+
+  // vector width: limited by head_dim, base alignment and strides of q, k and v
+  auto align_of = [](const void* ptr, std::initializer_list<int64_t> strides, int hd_) {
+    int vec = 8;
+    while (vec > 2) {
+      bool ok = (reinterpret_cast<uintptr_t>(ptr) % (vec * 2) == 0) && (hd_ % vec == 0);
+      for (int64_t s : strides) ok = ok && (s % vec == 0);
+      if (ok) break;
+      vec >>= 1;
+    }
+    return vec;
+  };
+  int vec = align_of(q, {q_strides[0], q_strides[1]}, hd);
+  vec = std::min(vec, align_of(k_cache, {k_strides[0], k_strides[1], k_strides[2]}, hd));
+  vec = std::min(vec, align_of(v_cache, {v_strides[0], v_strides[1], v_strides[2]}, hd));
+  {
+    bool ok2 = (reinterpret_cast<uintptr_t>(q) % 4 == 0) && (reinterpret_cast<uintptr_t>(k_cache) % 4 == 0) &&
+               (reinterpret_cast<uintptr_t>(v_cache) % 4 == 0);
+    for (int64_t s : {q_strides[0], q_strides[1], k_strides[0], k_strides[1], k_strides[2], v_strides[0],
+                      v_strides[1], v_strides[2]})
+      ok2 = ok2 && (s % 2 == 0);
+    if (!ok2) return fail(VATS_ERR_UNSUPPORTED, "decode needs 4-byte aligned rows (even strides, 4-byte aligned bases)");
+  }
+
+  const int hpg_tile = p.hpg >= 4 ? 4 : p.hpg;
+  p.head_batches = (p.hpg + hpg_tile - 1) / hpg_tile;
+  if ((long long)B * G > 65535 || p.head_batches > 65535)
+    return fail(VATS_ERR_UNSUPPORTED, "decode grid limit: B*G must be <= 65535 (got %lld)", (long long)B * G);
+  dim3 grid(p.num_splits, B * G, p.head_batches);
+  const size_t smem = (size_t)vats::kDecodeWarps * hpg_tile * hd * sizeof(float);
+
+  // lanes per key row: the smallest power of two covering hd / vec (<= 32, else several chunks per lane)
+  const int chunks = (hd + vec - 1) / vec;
+  rc = VATS_ERR_UNSUPPORTED;
+  if (vec == 8) {
+    if (chunks <= 4) rc = launch_decode_hpg<8, 4, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 8) rc = launch_decode_hpg<8, 8, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 16) rc = launch_decode_hpg<8, 16, 1>(p, hpg_tile, grid, smem, st);
+    else rc = launch_decode_hpg<8, 32, 1>(p, hpg_tile, grid, smem, st);
+  } else if (vec == 4) {
+    if (chunks <= 8) rc = launch_decode_hpg<4, 8, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 16) rc = launch_decode_hpg<4, 16, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 32) rc = launch_decode_hpg<4, 32, 1>(p, hpg_tile, grid, smem, st);
+    else rc = launch_decode_hpg<4, 32, 2>(p, hpg_tile, grid, smem, st);
+  } else {
+    if (chunks <= 16) rc = launch_decode_hpg<2, 16, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 32) rc = launch_decode_hpg<2, 32, 1>(p, hpg_tile, grid, smem, st);
+    else if (chunks <= 64) rc = launch_decode_hpg<2, 32, 2>(p, hpg_tile, grid, smem, st);
+    else rc = launch_decode_hpg<2, 32, 4>(p, hpg_tile, grid, smem, st);
+  }
+  if (rc != VATS_OK) return rc;
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  if (p.num_splits > 1) {
+    vats::decode_combine_kernel<<<B * H, 128, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches = 2;
+  }
+  return VATS_OK;
+}
+
+int vats_attn_debug_mask(uint8_t* out, const uint8_t* q_valid, const uint8_t* k_valid, int N, int Tq, int Tk,
+                         int causal, int left, int right, void* stream) {
+  if (N < 0 || Tq < 0 || Tk < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
+  int rc = check_device();
+  if (rc != VATS_OK) return rc;
+  if ((long long)N * Tq * Tk == 0) return VATS_OK;
+  if (!out) return fail(VATS_ERR_INVALID_ARGUMENT, "out must not be NULL");
+  vats::MaskParams mp{Tq, Tk, causal ? 1 : 0, left, right};
+  debug_mask_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, q_valid, k_valid, N, Tq, Tk, mp);
+  CUDA_TRY(cudaGetLastError());
+  return VATS_OK;
+}
+
+int vats_attn_debug_tile_range(int q0, int block_m, int block_n, int Tq, int Tk, int causal, int left, int right,
+                               int* first_tile, int* last_tile) {
+  if (!first_tile || !last_tile || block_m <= 0 || block_n <= 0)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "bad arguments");
+  vats::MaskParams mp{Tq, Tk, causal ? 1 : 0, left, right};
+  vats::tile_range(mp, q0, block_m, block_n, first_tile, last_tile);
+  return VATS_OK;
+}
+
+int vats_attn_debug_tile_is_full(int tile, int q0, int block_m, int block_n, int Tq, int Tk, int causal, int left,
+                                 int right) {
+  vats::MaskParams mp{Tq, Tk, causal ? 1 : 0, left, right};
+  return vats::tile_is_full(mp, tile, q0, block_m, block_n) ? 1 : 0;
+}
+
+}  // extern "C"

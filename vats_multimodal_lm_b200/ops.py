@@ -1,0 +1,160 @@
+"""``torch.library`` custom ops over the C-ABI library — the only compute entry points of the package.
+
+    torch.ops.vats.gqa_swa_prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel) -> o
+    torch.ops.vats.gqa_swa_decode(q, k_cache, v_cache, seq_lens, scale, left) -> o
+    ops.attn_mask(q_valid, k_valid, N, Tq, Tk, causal, left, right)   (plain function) -> uint8 [N,Tq,Tk]
+
+They replace the reference's single library call ``F.scaled_dot_product_attention``
+(src/optimized_attention.py:709-714, vit_2d/optimized_attention.py:396-402, vit_3d/optimized_attention.py:302-307)
+plus the K/V head expansion in front of it (utils/attention_utils.py:7-27).  Tensors must live on a CUDA (sm_100)
+device in bf16; anything else raises — there is deliberately no eager / CPU path here.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _ffi
+
+__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
+
+KERNEL_AUTO = _ffi.KERNEL_AUTO
+KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
+KERNEL_SIMT = _ffi.KERNEL_SIMT
+
+
+def _require_cuda_bf16(name: str, t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"vats attention ops run only on a CUDA sm_100 device; `{name}` is on {t.device}. "
+            "There is no CPU fallback (use oracle/ for CPU checking in tests)."
+        )
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError(f"`{name}` must be bfloat16, got {t.dtype}")
+
+
+def _rowmajor_last(t: torch.Tensor) -> torch.Tensor:
+    """Kernels need the head_dim axis contiguous; every other stride is passed through."""
+    return t if t.stride(-1) == 1 or t.size(-1) == 1 else t.contiguous()
+
+
+def _valid_u8(name: str, m: Optional[torch.Tensor], N: int, T: int, device) -> Optional[torch.Tensor]:
+    if m is None:
+        return None
+    if m.shape != (N, T):
+        raise ValueError(f"`{name}` must have shape {(N, T)}, got {tuple(m.shape)}")
+    if m.device != device:
+        raise RuntimeError(f"`{name}` must be on {device}")
+    if m.dtype == torch.bool:
+        return m.contiguous().view(torch.uint8)
+    return (m != 0).to(torch.uint8).contiguous()
+
+
+@torch.library.custom_op("vats::gqa_swa_prefill", mutates_args=(), device_types="cuda")
+def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: Optional[torch.Tensor],
+                    k_valid: Optional[torch.Tensor], scale: float, causal: bool, left: int, right: int,
+                    kernel: int = 0) -> torch.Tensor:
+    """q [N,Tq,H,hd], k/v [N,Tk,G,hd] (bf16, any strides with hd contiguous) -> o [N,Tq,H,hd] bf16."""
+    _require_cuda_bf16("q", q)
+    _require_cuda_bf16("k", k)
+    _require_cuda_bf16("v", v)
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError("q, k, v must be 4-D [N, T, heads, head_dim]")
+    N, Tq, H, hd = q.shape
+    Nk, Tk, G, hdk = k.shape
+    if v.shape != k.shape or Nk != N or hdk != hd:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
+    if G <= 0 or H % G != 0:
+        raise ValueError(f"num_heads ({H}) must be divisible by query_groups ({G})")
+    q, k, v = _rowmajor_last(q), _rowmajor_last(k), _rowmajor_last(v)
+    qv = _valid_u8("q_valid", q_valid, N, Tq, q.device)
+    kv = _valid_u8("k_valid", k_valid, N, Tk, q.device)
+    o = torch.empty((N, Tq, H, hd), dtype=torch.bfloat16, device=q.device)
+    if o.numel() == 0:
+        return o
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.prefill(q.data_ptr(), k.data_ptr() if k.numel() else None, v.data_ptr() if v.numel() else None,
+                     o.data_ptr(), qv.data_ptr() if qv is not None else None,
+                     kv.data_ptr() if kv is not None else None,
+                     N, Tq, Tk, H, G, hd, q.stride()[:3], k.stride()[:3], v.stride()[:3], o.stride()[:3],
+                     scale, causal, left, right, stream, kernel)
+    return o
+
+
+@gqa_swa_prefill.register_fake
+def _(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
+    return q.new_empty(q.shape, dtype=torch.bfloat16)
+
+
+@torch.library.custom_op("vats::gqa_swa_decode", mutates_args=(), device_types="cuda")
+def gqa_swa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_lens: torch.Tensor,
+                   scale: float, left: int) -> torch.Tensor:
+    """q [B,H,hd], caches [B,S_max,G,hd] bf16, seq_lens [B] int32 (valid tokens incl. the new one) -> o [B,H,hd]."""
+    _require_cuda_bf16("q", q)
+    _require_cuda_bf16("k_cache", k_cache)
+    _require_cuda_bf16("v_cache", v_cache)
+    if q.dim() != 3 or k_cache.dim() != 4 or v_cache.shape != k_cache.shape:
+        raise ValueError("q must be [B,H,hd]; k_cache and v_cache must be [B,S_max,G,hd] with equal shapes")
+    B, H, hd = q.shape
+    Bc, S_max, G, hdc = k_cache.shape
+    if Bc != B or hdc != hd:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} cache {tuple(k_cache.shape)}")
+    if G <= 0 or H % G != 0:
+        raise ValueError(f"num_heads ({H}) must be divisible by query_groups ({G})")
+    if seq_lens.shape != (B,) or seq_lens.dtype != torch.int32 or seq_lens.device != q.device:
+        raise ValueError("seq_lens must be an int32 tensor of shape [B] on the same device")
+    q = _rowmajor_last(q)
+    if k_cache.stride(-1) != 1 or v_cache.stride(-1) != 1:
+        raise ValueError("KV cache must have a contiguous head_dim axis (refusing to copy a cache)")
+    seq_lens = seq_lens.contiguous()
+    o = torch.empty((B, H, hd), dtype=torch.bfloat16, device=q.device)
+    if o.numel() == 0:
+        return o
+    ws_bytes = _ffi.decode_workspace_bytes(B, H, G, hd, S_max, left)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), o.data_ptr(), seq_lens.data_ptr(),
+                    B, H, G, hd, S_max, q.stride()[:2], k_cache.stride()[:3], v_cache.stride()[:3], o.stride()[:2],
+                    scale, left, ws.data_ptr(), ws.numel(), stream)
+    return o
+
+
+@gqa_swa_decode.register_fake
+def _(q, k_cache, v_cache, seq_lens, scale, left):
+    return q.new_empty(q.shape, dtype=torch.bfloat16)
+
+
+def attn_mask(q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], N: int, Tq: int, Tk: int,
+              causal: bool, left: int, right: int, device: Optional[torch.device] = None) -> torch.Tensor:
+    """The kernels' own mask predicate, materialised (uint8 [N,Tq,Tk]); used for the bit-exact mask tests."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("attn_mask runs the device predicate and needs a CUDA device")
+    qv = _valid_u8("q_valid", q_valid, N, Tq, device)
+    kv = _valid_u8("k_valid", k_valid, N, Tk, device)
+    out = torch.empty((N, Tq, Tk), dtype=torch.uint8, device=device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.debug_mask(out.data_ptr(), qv.data_ptr() if qv is not None else None,
+                        kv.data_ptr() if kv is not None else None, N, Tq, Tk, causal, left, right, stream)
+    return out
+
+
+def _no_cpu(name):
+    def impl(*args, **kwargs):
+        raise RuntimeError(
+            f"torch.ops.vats.{name} has no CPU implementation: the attention core runs only on a CUDA sm_100 device "
+            "(hand-written kernels, no fallback). Move the tensors to the GPU."
+        )
+    return impl
+
+
+gqa_swa_prefill.register_kernel("cpu")(_no_cpu("gqa_swa_prefill"))
+gqa_swa_decode.register_kernel("cpu")(_no_cpu("gqa_swa_decode"))
