@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 run() { # name, timeout, pytest args...
   local name=$1; local to=$2; shift 2
-  timeout "$to" python -m pytest "$@" -q -x --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
+  timeout "$to" python -m pytest "$@" -q --maxfail=4 --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   echo "== $name exit $? =="; tail -n 25 "gpurun_out/$name.log"
 }
 run safe 600 tests/test_gpu_ops.py -m gpu -k "simt or decode or mask or empty or launch"

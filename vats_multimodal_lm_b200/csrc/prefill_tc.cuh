@@ -12,7 +12,10 @@
 //   warps 0-3   softmax warpgroup of tile 0: thread r owns S row r (TMEM lane r) — row max / row sum are in-thread
 //   warps 4-7   softmax warpgroup of tile 1
 //   warp  8     TMA producer: Q tiles once, then K_j, V_j into mbarrier-guarded rings (128B-swizzled boxes)
-//   warp  9     MMA issuer (one elected lane): S = Q·K^T (SS, both K-major), O += P·V (TS: P from TMEM, V MN-major)
+//   warps 8-10  (only for head dims TMA cannot address, e.g. 60 or 66: rows are 4-byte, not 16-byte, aligned)
+//               LDG staging loaders: coalesced 32-bit loads, stored into the same 128B-swizzled layout
+//   warp  11    MMA issuer (one elected lane): S = Q·K^T (SS, both K-major), O += P·V (TS: P from TMEM, V MN-major)
+//   Registers are re-balanced with setmaxnreg: 80 for warps 8-11, 208 for the softmax warps.
 //
 //   TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (bf16) aliases the first 64 columns of S.
 //
@@ -28,7 +31,8 @@ namespace vats {
 
 constexpr int kTcBlockM = 128;
 constexpr int kTcBlockN = 128;
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 384;
+constexpr int kTcLoaderThreads = 96;  // warps 8-10 in LDG staging mode
 constexpr int kTcRegionBytes = 128 * 128;  // 128 rows x 64 bf16, one 128B-swizzled box
 constexpr int kTcMaxStages = 4;
 constexpr float kTcRescaleThreshold = 8.0f;  // log2 units
@@ -40,8 +44,7 @@ struct TcParams {
   int q_blocks;      // ceil(Tq / 128)
   int pairs;         // ceil(hpg / 2) head pairs per KV group
   int nk, nv;        // ring depths
-  int merged_q, merged_kv;  // 1: tensor map inner dim is heads*hd and the head is selected by the inner coordinate
-  int q_fixup;       // 1: zero the Q columns [hd, hd_pad) in smem (merged map fetched neighbour-head data there)
+  int q_ldg, kv_ldg; // 1: the tensor is not TMA-addressable (row starts only 4-byte aligned): LDG staging instead
   int o_vec16;       // 1: O rows may be written with 16-byte stores
 };
 
@@ -59,6 +62,59 @@ struct TcSmemBarriers {
 
 __host__ __device__ inline size_t tc_smem_bytes(int regions, int nk, int nv) {
   return (size_t)(2 + nk + nv) * regions * kTcRegionBytes + 1024 /*alignment slack*/ + sizeof(TcSmemBarriers);
+}
+
+// Stage rows [row0, row0+128) x hd of a row-strided bf16 matrix into a 128B-swizzled K-major tile (the layout a
+// (64 x 128) SWIZZLE_128B TMA box would produce), with 32-bit loads.  Rows >= T and columns [hd, hd_pad) are zero.
+template <int NT>
+__device__ __forceinline__ void ldg_stage_tile(unsigned char* dst, const __nv_bfloat16* src, long long stride_t,
+                                               int row0, int T, int hd, int hd_pad, int tid) {
+  const int wpr = hd_pad >> 1;  // 32-bit words per staged row
+  const int hw = hd >> 1;       // valid words per row
+  // word index idx = r * wpr + w walks tid, tid + NT, ...; (r, w) advance incrementally (no per-word division)
+  const int dq = NT / wpr, dr = NT % wpr;
+  int r_l = tid / wpr, w_l = tid - r_l * wpr;  // load cursor
+  int r_s = r_l, w_s = w_l;                    // store cursor
+  constexpr int UNR = 8;
+  while (r_s < 128) {
+    uint32_t val[UNR];
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      val[i] = 0u;
+      if (r_l < 128 && (row0 + r_l) < T && w_l < hw)
+        val[i] = ptx::ldg_nc_u32(src + (long long)(row0 + r_l) * stride_t + 2 * w_l);
+      w_l += dr;
+      r_l += dq;
+      if (w_l >= wpr) {
+        w_l -= wpr;
+        ++r_l;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < UNR; ++i) {
+      if (r_s < 128) {
+        const uint32_t r = (uint32_t)r_s, w = (uint32_t)w_s;
+        const uint32_t wi = w & 31u;
+        const uint32_t off = (w >> 5) * kTcRegionBytes + r * 128u + (((wi >> 2) ^ (r & 7u)) << 4) + ((wi & 3u) << 2);
+        *reinterpret_cast<uint32_t*>(dst + off) = val[i];
+      }
+      w_s += dr;
+      r_s += dq;
+      if (w_s >= wpr) {
+        w_s -= wpr;
+        ++r_s;
+      }
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -109,16 +165,17 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->s_full[t]), 1);
       mbar_init(smem_u32(&bars->p_full[t]), 128);
     }
+    const uint32_t kv_arrivals = P.kv_ldg ? kTcLoaderThreads : 1;
     for (int s = 0; s < kTcMaxStages; ++s) {
-      mbar_init(smem_u32(&bars->k_full[s]), 1);
+      mbar_init(smem_u32(&bars->k_full[s]), kv_arrivals);
       mbar_init(smem_u32(&bars->k_empty[s]), 1);
-      mbar_init(smem_u32(&bars->v_full[s]), 1);
+      mbar_init(smem_u32(&bars->v_full[s]), kv_arrivals);
       mbar_init(smem_u32(&bars->v_empty[s]), 1);
     }
     mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == 11) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -127,49 +184,68 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
-    // =========================================================== TMA producer
-    if (lane == 0 && n_tiles > 0) {
+  if (warp >= 8) {
+    // =========================================================== warpgroup 2: producers (warps 8-10) + MMA issuer (11)
+    setmaxnreg_dec<80>();
+  if (warp <= 10) {
+    if (warp == 8 && lane == 0 && n_tiles > 0 && !P.q_ldg) {
       for (int t = 0; t < 2; ++t) {
         if (t == 1 && !active1) break;
         const uint32_t bar = smem_u32(&bars->q_full[t]);
         mbar_expect_tx(bar, tile_bytes);
-        const int h = head0 + t;
-        for (int c = 0; c < P.regions; ++c) {
-          const int c0 = P.merged_q ? h * a.hd + 64 * c : 64 * c;
-          const int c1 = P.merged_q ? 0 : h;
-          tma_load_4d(sQ + t * tile_bytes + c * kTcRegionBytes, &tmap_q, bar, c0, c1, q0, n);
+        for (int c = 0; c < P.regions; ++c)
+          tma_load_4d(sQ + t * tile_bytes + c * kTcRegionBytes, &tmap_q, bar, 64 * c, head0 + t, q0, n);
+      }
+    }
+    if (!P.kv_ldg) {
+      // ---- TMA: one elected lane feeds the K and V rings
+      if (warp == 8 && lane == 0) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int k0 = (t_first + j) * kTcBlockN;
+          {
+            const int s = j % P.nk;
+            mbar_wait(smem_u32(&bars->k_empty[s]), ((uint32_t)(j / P.nk) & 1u) ^ 1u);
+            const uint32_t bar = smem_u32(&bars->k_full[s]);
+            mbar_expect_tx(bar, tile_bytes);
+            for (int c = 0; c < P.regions; ++c)
+              tma_load_4d(sK + s * tile_bytes + c * kTcRegionBytes, &tmap_k, bar, 64 * c, g, k0, n);
+          }
+          {
+            const int s = j % P.nv;
+            mbar_wait(smem_u32(&bars->v_empty[s]), ((uint32_t)(j / P.nv) & 1u) ^ 1u);
+            const uint32_t bar = smem_u32(&bars->v_full[s]);
+            mbar_expect_tx(bar, tile_bytes);
+            for (int c = 0; c < P.regions; ++c)
+              tma_load_4d(sV + s * tile_bytes + c * kTcRegionBytes, &tmap_v, bar, 64 * c, g, k0, n);
+          }
         }
       }
+    } else {
+      // ---- LDG staging: 96 threads copy each K / V tile into the swizzled layout
+      const int ltid = threadIdx.x - 8 * 32;
+      const __nv_bfloat16* kbase = a.k + n * a.ks_n + (long long)g * a.ks_h;
+      const __nv_bfloat16* vbase = a.v + n * a.vs_n + (long long)g * a.vs_h;
+      unsigned char* sK_g = smem_raw + (sK - raw);
+      unsigned char* sV_g = smem_raw + (sV - raw);
       for (int j = 0; j < n_tiles; ++j) {
         const int k0 = (t_first + j) * kTcBlockN;
         {
           const int s = j % P.nk;
-          const uint32_t ph = (uint32_t)(j / P.nk) & 1u;
-          mbar_wait(smem_u32(&bars->k_empty[s]), ph ^ 1u);
-          const uint32_t bar = smem_u32(&bars->k_full[s]);
-          mbar_expect_tx(bar, tile_bytes);
-          for (int c = 0; c < P.regions; ++c) {
-            const int c0 = P.merged_kv ? g * a.hd + 64 * c : 64 * c;
-            const int c1 = P.merged_kv ? 0 : g;
-            tma_load_4d(sK + s * tile_bytes + c * kTcRegionBytes, &tmap_k, bar, c0, c1, k0, n);
-          }
+          mbar_wait(smem_u32(&bars->k_empty[s]), ((uint32_t)(j / P.nk) & 1u) ^ 1u);
+          ldg_stage_tile<kTcLoaderThreads>(sK_g + (size_t)s * tile_bytes, kbase, a.ks_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&bars->k_full[s]));
         }
         {
           const int s = j % P.nv;
-          const uint32_t ph = (uint32_t)(j / P.nv) & 1u;
-          mbar_wait(smem_u32(&bars->v_empty[s]), ph ^ 1u);
-          const uint32_t bar = smem_u32(&bars->v_full[s]);
-          mbar_expect_tx(bar, tile_bytes);
-          for (int c = 0; c < P.regions; ++c) {
-            const int c0 = P.merged_kv ? g * a.hd + 64 * c : 64 * c;
-            const int c1 = P.merged_kv ? 0 : g;
-            tma_load_4d(sV + s * tile_bytes + c * kTcRegionBytes, &tmap_v, bar, c0, c1, k0, n);
-          }
+          mbar_wait(smem_u32(&bars->v_empty[s]), ((uint32_t)(j / P.nv) & 1u) ^ 1u);
+          ldg_stage_tile<kTcLoaderThreads>(sV_g + (size_t)s * tile_bytes, vbase, a.vs_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&bars->v_full[s]));
         }
       }
     }
-  } else if (warp == 9) {
+  } else {
     // =========================================================== MMA issuer
     if (lane == 0 && n_tiles > 0) {
       const uint32_t idesc_s = make_idesc_bf16(kTcBlockM, kTcBlockN, 0, 0);
@@ -196,8 +272,8 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       };
 
       for (int t = 0; t < ntile_heads; ++t) {
-        mbar_wait(smem_u32(&bars->q_full[t]), 0);
-        if (P.q_fixup) mbar_wait(smem_u32(&bars->q_fixed[t]), 0);
+        if (P.q_ldg) mbar_wait(smem_u32(&bars->q_fixed[t]), 0);
+        else mbar_wait(smem_u32(&bars->q_full[t]), 0);
       }
       mbar_wait(smem_u32(&bars->k_full[0]), 0);
       tc_fence_after();
@@ -230,8 +306,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       }
       tc_commit(smem_u32(&bars->o_full));
     }
+  }
   } else {
     // =========================================================== softmax warpgroups (tile t = warp / 4)
+    setmaxnreg_inc<208>();
     const int t = warp >> 2;
     const int r = threadIdx.x & 127;           // row within the tile == TMEM lane
     const int tok = q0 + r;
@@ -245,15 +323,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     float m_used = -INFINITY;  // reference maximum in scaled-log2 units; -inf = not set yet
 
     if (tile_active && n_tiles > 0) {
-      if (P.q_fixup) {
-        mbar_wait(smem_u32(&bars->q_full[t]), 0);
-        unsigned char* qrow = smem_raw + (sQ - raw) + t * tile_bytes;
-        for (int c = a.hd; c < P.hd_pad; ++c) {
-          const int cw = c & 63;
-          const uint32_t off = (uint32_t)(c >> 6) * kTcRegionBytes + (uint32_t)r * 128u +
-                               ((((uint32_t)cw * 2u) >> 4) ^ ((uint32_t)r & 7u)) * 16u + (((uint32_t)cw * 2u) & 15u);
-          *reinterpret_cast<uint16_t*>(qrow + off) = 0;
-        }
+      if (P.q_ldg) {
+        // the 128 threads of this warpgroup stage their own Q tile (once per CTA)
+        const __nv_bfloat16* qbase = a.q + n * a.qs_n + (long long)head * a.qs_h;
+        ldg_stage_tile<128>(smem_raw + (sQ - raw) + (size_t)t * tile_bytes, qbase, a.qs_t, q0, a.Tq, a.hd, P.hd_pad, r);
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bars->q_fixed[t]));
       }
@@ -402,7 +475,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 11) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 // Bounded wait: a barrier that has not completed after ~4 s of wall clock is a protocol bug — trap (the launch
 // fails with an error) instead of hanging the GPU.  The timer is only read every 4096 polls.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {

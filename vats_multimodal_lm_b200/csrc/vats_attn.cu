@@ -76,55 +76,31 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// A [N, T, heads, hd] bf16 tensor (strides in elements, hd contiguous) as a 4-D tiled map with a
-// (64 x 1 x 128 x 1) box, 128-byte swizzle.
-//   split  mode: dims (hd, heads, T, N)          — needs the head stride to be a multiple of 8 elements
-//   merged mode: dims (heads*hd, 1, T, N)        — heads contiguous (stride == hd); the head is picked by the inner
-//                                                   coordinate, which lets head dims like 60 or 66 through TMA
-struct MapPlan {
-  bool ok;
-  bool merged;
-};
+// A [N, T, heads, hd] bf16 tensor (strides in elements, hd contiguous) as a 4-D tiled map, dims (hd, heads, T, N),
+// box (64 x 1 x 128 x 1), 128-byte swizzle; columns past hd and rows past T are zero-filled by TMA.
+// TMA needs a 16-byte aligned base and every stride a multiple of 16 bytes (8 elements) — and the box start address
+// (base + coordinates) 16-byte aligned too, which rules out selecting a head through an unaligned inner coordinate.
+// Head dims such as 60 or 66 therefore cannot use TMA; they go through the kernel's LDG staging path, which only
+// needs 4-byte aligned rows (even strides).
+enum class LoadMode { kNone, kTma, kLdg };
 
-MapPlan plan_map(const void* ptr, int heads, int hd, const int64_t s[3]) {
-  MapPlan r{false, false};
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return r;
-  if (s[0] % 8 != 0 || s[1] % 8 != 0) return r;
-  if (s[2] % 8 == 0) {
-    r.ok = true;
-    r.merged = false;
-    return r;
-  }
-  if (s[2] == hd || heads == 1) {
-    r.ok = true;
-    r.merged = true;
-    return r;
-  }
-  return r;
+LoadMode plan_load(const void* ptr, int hd, const int64_t s[3]) {
+  const bool tma = (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0;
+  if (tma) return LoadMode::kTma;
+  const bool ldg = (reinterpret_cast<uintptr_t>(ptr) & 3u) == 0 && hd % 2 == 0 && s[0] % 2 == 0 && s[1] % 2 == 0 &&
+                   s[2] % 2 == 0;
+  return ldg ? LoadMode::kLdg : LoadMode::kNone;
 }
 
-int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3], bool merged) {
+int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3]) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint64_t dims[4];
-  cuuint64_t strides[3];
-  if (merged) {
-    dims[0] = (cuuint64_t)heads * hd;
-    dims[1] = 1;
-    strides[0] = (cuuint64_t)(s[1] > 0 ? s[1] : (int64_t)heads * hd) * 2;  // unused (dim 1 has extent 1)
-  } else {
-    dims[0] = (cuuint64_t)hd;
-    dims[1] = (cuuint64_t)heads;
-    strides[0] = (cuuint64_t)s[2] * 2;
-  }
-  dims[2] = (cuuint64_t)T;
-  dims[3] = (cuuint64_t)N;
-  strides[1] = (cuuint64_t)s[1] * 2;
-  strides[2] = (cuuint64_t)s[0] * 2;
-  // extent-1 dimensions may carry a zero stride in PyTorch; give TMA something legal
-  if (T == 1 || strides[1] == 0) strides[1] = (cuuint64_t)heads * hd * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)heads, (cuuint64_t)T, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)s[2] * 2, (cuuint64_t)s[1] * 2, (cuuint64_t)s[0] * 2};
+  // extent-1 dimensions may carry any stride in PyTorch; give TMA something legal
+  if (heads == 1 || strides[0] == 0) strides[0] = (cuuint64_t)((hd + 7) / 8 * 8) * 2;
+  if (T == 1 || strides[1] == 0) strides[1] = strides[0] * (cuuint64_t)heads;
   if (N == 1 || strides[2] == 0) strides[2] = strides[1] * (cuuint64_t)T;
-  if (strides[0] == 0) strides[0] = (cuuint64_t)hd * 2;
   const cuuint32_t box[4] = {64, 1, 128, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -162,15 +138,16 @@ int validate_prefill(const PrefillArgs& A) {
   return VATS_OK;
 }
 
-bool tc_legal(const PrefillArgs& A, MapPlan* pq, MapPlan* pk, MapPlan* pv) {
+struct TcPlan {
+  LoadMode q, k, v;
+};
+
+bool tc_legal(const PrefillArgs& A, TcPlan* pl) {
   if (A.hd > 128 || A.Tk <= 0) return false;
-  *pq = plan_map(A.q, A.H, A.hd, A.qs);
-  *pk = plan_map(A.k, A.G, A.hd, A.ks);
-  *pv = plan_map(A.v, A.G, A.hd, A.vs);
-  if (!pq->ok || !pk->ok || !pv->ok) return false;
-  // TMA coordinates are int32
-  if ((long long)A.H * A.hd > 0x7fffffffLL) return false;
-  return true;
+  pl->q = plan_load(A.q, A.hd, A.qs);
+  pl->k = plan_load(A.k, A.hd, A.ks);
+  pl->v = plan_load(A.v, A.hd, A.vs);
+  return pl->q != LoadMode::kNone && pl->k != LoadMode::kNone && pl->v != LoadMode::kNone;
 }
 
 void fill_common(vats::PrefillParams& p, const PrefillArgs& A) {
@@ -227,7 +204,7 @@ int launch_simt(const PrefillArgs& A, cudaStream_t st) {
   return VATS_OK;
 }
 
-int launch_tc(const PrefillArgs& A, const MapPlan& pq, const MapPlan& pk, const MapPlan& pv, cudaStream_t st) {
+int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   vats::TcParams P;
   std::memset(&P, 0, sizeof(P));
   fill_common(P.a, A);
@@ -235,11 +212,8 @@ int launch_tc(const PrefillArgs& A, const MapPlan& pq, const MapPlan& pk, const 
   P.regions = (P.hd_pad + 63) / 64;
   P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
   P.pairs = (P.a.hpg + 1) / 2;
-  P.merged_q = pq.merged ? 1 : 0;
-  P.merged_kv = pk.merged ? 1 : 0;
-  if (pk.merged != pv.merged) return fail(VATS_ERR_UNSUPPORTED, "k and v must share the same head layout class");
-  // A merged map fetches the neighbouring head's first elements into the padding columns; a split map zero-fills them.
-  P.q_fixup = (pq.merged && P.hd_pad != A.hd) ? 1 : 0;
+  P.q_ldg = pl.q == LoadMode::kLdg ? 1 : 0;
+  P.kv_ldg = (pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg) ? 1 : 0;
   P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1
@@ -256,10 +230,15 @@ int launch_tc(const PrefillArgs& A, const MapPlan& pq, const MapPlan& pk, const 
   const size_t smem = vats::tc_smem_bytes(P.regions, nk, nv);
 
   CUtensorMap mq, mk, mv;
+  std::memset(&mq, 0, sizeof(mq));
+  std::memset(&mk, 0, sizeof(mk));
+  std::memset(&mv, 0, sizeof(mv));
   int rc;
-  if ((rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs, pq.merged)) != VATS_OK) return rc;
-  if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks, pk.merged)) != VATS_OK) return rc;
-  if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs, pv.merged)) != VATS_OK) return rc;
+  if (!P.q_ldg && (rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs)) != VATS_OK) return rc;
+  if (!P.kv_ldg) {
+    if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks)) != VATS_OK) return rc;
+    if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs)) != VATS_OK) return rc;
+  }
 
   const long long ctas = (long long)A.N * A.G * P.pairs * P.q_blocks;
   if (ctas > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "grid too large");
@@ -274,8 +253,8 @@ int launch_tc(const PrefillArgs& A, const MapPlan& pq, const MapPlan& pk, const 
   return VATS_OK;
 }
 
-int choose_kernel(const PrefillArgs& A, MapPlan* pq, MapPlan* pk, MapPlan* pv) {
-  const bool legal = tc_legal(A, pq, pk, pv);
+int choose_kernel(const PrefillArgs& A, TcPlan* pl) {
+  const bool legal = tc_legal(A, pl);
   if (!legal) return VATS_KERNEL_SIMT;
   // Tiles are 128 x 128: below 32 keys or 32 query tokens more than 3/4 of every MMA would be padding and the
   // problem is bandwidth-bound anyway (ViT-3D temporal pass: 8 tokens per sequence).
@@ -290,16 +269,16 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
   if ((rc = check_device()) != VATS_OK) return rc;
   if (A.N == 0 || A.Tq == 0) return VATS_OK;  // empty output (reference: T == 0 returns an empty tensor, :405-407)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MapPlan pq{false, false}, pk{false, false}, pv{false, false};
-  int auto_choice = choose_kernel(A, &pq, &pk, &pv);
+  TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
+  int auto_choice = choose_kernel(A, &pl);
   if (kernel == VATS_KERNEL_AUTO) kernel = auto_choice;
   if (kernel == VATS_KERNEL_TCGEN05) {
-    if (!tc_legal(A, &pq, &pk, &pv))
+    if (!tc_legal(A, &pl))
       return fail(VATS_ERR_UNSUPPORTED,
-                  "geometry is not TMA-legal for the tcgen05 kernel (hd=%d, need hd<=128, 16-byte aligned base and "
-                  "token/sequence strides, heads contiguous or head stride %% 8 == 0)",
+                  "geometry not supported by the tcgen05 kernel (hd=%d: need 1 <= Tk, even hd <= 128, even strides and "
+                  "4-byte aligned bases)",
                   A.hd);
-    return launch_tc(A, pq, pk, pv, st);
+    return launch_tc(A, pl, st);
   }
   if (kernel == VATS_KERNEL_SIMT) return launch_simt(A, st);
   return fail(VATS_ERR_INVALID_ARGUMENT, "unknown kernel selector %d", kernel);
@@ -375,8 +354,8 @@ int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd, const in
   PrefillArgs A{q, k, v, nullptr, nullptr, nullptr, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
                 1.f, 0, -1, -1};
   if (H <= 0 || G <= 0 || hd <= 0 || H % G != 0 || !q_strides || !k_strides || !v_strides) return -1;
-  MapPlan pq, pk, pv;
-  return choose_kernel(A, &pq, &pk, &pv);
+  TcPlan pl;
+  return choose_kernel(A, &pl);
 }
 
 size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left) {
