@@ -219,8 +219,14 @@ def bench_decode(args, world, peaks):
     dev = torch.device("cuda", torch.cuda.current_device())
     rank = dist_env()[0]
     B, S, H, G, hd, left = c["B"], c["S"], c["H"], c["G"], c["hd"], c["left"]
-    kc = gen_unit_bf16((B, S, G, hd), 1234 + 2 + 100 * rank, dev, True)
-    vc = gen_unit_bf16((B, S, G, hd), 2234 + 2 + 100 * rank, dev, False)
+    if args.cache_layout == "bhsd":
+        # head-major storage [B, G, S, hd] exposed with the reference's [B, S, G, hd] shape (a strided view): every
+        # (sequence, KV group) is one contiguous 1 MB run of keys — the layout the drop-in KVCache allocates
+        kc = gen_unit_bf16((B, G, S, hd), 1234 + 2 + 100 * rank, dev, True).permute(0, 2, 1, 3)
+        vc = gen_unit_bf16((B, G, S, hd), 2234 + 2 + 100 * rank, dev, False).permute(0, 2, 1, 3)
+    else:
+        kc = gen_unit_bf16((B, S, G, hd), 1234 + 2 + 100 * rank, dev, True)
+        vc = gen_unit_bf16((B, S, G, hd), 2234 + 2 + 100 * rank, dev, False)
     q = gen_unit_bf16((B, H, hd), 3234 + 2 + 100 * rank, dev, True)
     lens = torch.full((B,), S, dtype=torch.int32, device=dev)
     scale = hd ** -0.5
@@ -429,6 +435,7 @@ def run_ours(args):
                 "bytes_per_step_per_gpu": decode_bytes(CFG2), "flops_per_step_per_gpu": decode_flops(CFG2),
                 "l2": "inputs larger than L2 (1.07 GB of K/V streamed per step vs 126 MB L2)",
                 "parallelism": f"batch-sharded x{world}, caches stay sharded, no collective",
+                "cache_layout": args.cache_layout,
             },
             "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["launches"], "roofline": r["roofline"],
             "device_ms_per_step": r["dev_ms"],
@@ -447,6 +454,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--cache-layout", default="bshd", choices=["bshd", "bhsd"],
+                    help="storage order of the KV cache behind its [B,S,G,hd] shape")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -242,8 +242,37 @@ def test_decode_equals_prefill_last_row():
 
 
 def test_launch_count_reported():
+    # TMA-addressable cache -> mma.sync kernel, splits merged by the last CTA: one launch
     q, kc, vc = _mk_cache(2, 600, 2, 64, 4, seed=1)
     ops.gqa_swa_decode(q.cuda(), kc.cuda(), vc.cuda(), torch.tensor([600, 600], dtype=torch.int32).cuda(), 0.1, -1)
-    assert _ffi.last_launch_count() == 2        # split kernel + combine
+    assert _ffi.last_launch_count() == 1
+    # hd 60 is not TMA-addressable -> CUDA-core kernel: split kernel + combine, or one launch for a single split
+    q, kc, vc = _mk_cache(2, 600, 2, 60, 4, seed=1)
+    ops.gqa_swa_decode(q.cuda(), kc.cuda(), vc.cuda(), torch.tensor([600, 600], dtype=torch.int32).cuda(), 0.1, -1)
+    assert _ffi.last_launch_count() == 2
     ops.gqa_swa_decode(q.cuda(), kc.cuda(), vc.cuda(), torch.tensor([600, 600], dtype=torch.int32).cuda(), 0.1, 100)
-    assert _ffi.last_launch_count() == 1        # single split: written directly
+    assert _ffi.last_launch_count() == 1
+
+
+def test_decode_workspace_is_reusable_across_calls():
+    """The split counters in the workspace are left at zero: repeated calls (and a different window) stay correct."""
+    B, S, H, G, hd = 3, 2000, 16, 4, 128
+    q, kc, vc = _mk_cache(B, S, G, hd, H, seed=5)
+    dq, dk, dv = q.cuda(), kc.cuda(), vc.cuda()
+    for lens, left in [([2000, 1500, 900], -1), ([2000, 1500, 900], -1), ([1999, 3, 1000], 700), ([2000, 2000, 0], 64)]:
+        sl = torch.tensor(lens, dtype=torch.int32)
+        o = ops.gqa_swa_decode(dq, dk, dv, sl.cuda(), 0.09, left)
+        check_close(o, decode_explicit(q, kc, vc, sl, 0.09, left), f"reuse {lens} {left}")
+
+
+def test_decode_stale_rows_past_sequence_end_do_not_leak():
+    """Cache rows beyond seq_len may hold anything (here NaN): they must not reach the output."""
+    B, S, H, G, hd = 2, 300, 8, 2, 128
+    q, kc, vc = _mk_cache(B, S, G, hd, H, seed=6)
+    lens = torch.tensor([137, 290], dtype=torch.int32)
+    kd, vd = kc.clone(), vc.clone()
+    for b, L in enumerate(lens.tolist()):
+        kd[b, L:] = float("nan")
+        vd[b, L:] = float("nan")
+    o = ops.gqa_swa_decode(q.cuda(), kd.cuda(), vd.cuda(), lens.cuda(), 0.09, -1)
+    check_close(o, decode_explicit(q, kc, vc, lens, 0.09, -1), "stale rows")

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Run one named workload a few times (for ncu captures): python tools/run_workload.py cfg5 [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vats_multimodal_lm_b200 import ops  # noqa: E402
+
+
+def rnd(shape, seed, norm):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(shape, generator=g, device="cuda")
+    if norm:
+        x = torch.nn.functional.normalize(x, dim=-1)
+    return x.bfloat16()
+
+
+W = {
+    # name: (N, T, H, G, hd, causal, left)
+    "cfg1": (1, 4096, 24, 8, 60, True, 384),
+    "cfg3": (256, 196, 16, 8, 72, False, -1),
+    "cfg4a": (512, 196, 32, 8, 66, False, -1),
+    "cfg4b": (12544, 8, 32, 8, 66, False, -1),
+    "cfg5": (1, 32768, 32, 8, 128, True, 4096),
+    "cfg5b2": (2, 32768, 32, 8, 128, True, 4096),
+}
+
+
+def main():
+    name = sys.argv[1]
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    if name == "cfg2":
+        B, S, H, G, hd, left = 64, 8192, 32, 8, 128, 4096
+        kc, vc, q = rnd((B, S, G, hd), 1, True), rnd((B, S, G, hd), 2, False), rnd((B, H, hd), 3, True)
+        lens = torch.full((B,), S, dtype=torch.int32, device="cuda")
+        for _ in range(reps):
+            o = ops.gqa_swa_decode(q, kc, vc, lens, hd ** -0.5, left)
+    else:
+        N, T, H, G, hd, causal, left = W[name]
+        q, k, v = rnd((N, T, H, hd), 1, True), rnd((N, T, G, hd), 2, True), rnd((N, T, G, hd), 3, False)
+        for _ in range(reps):
+            o = ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0)
+    torch.cuda.synchronize()
+    print(name, "ok", float(o.float().abs().mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#ifndef VATS_MBAR_TIMEOUT_CYCLES
+#define VATS_MBAR_TIMEOUT_CYCLES 30000000000ll
+#endif
+
 namespace vats {
 namespace ptx {
 
@@ -52,27 +56,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a barrier that has not completed after ~4 s of wall clock is a protocol bug — trap (the launch
-// fails with an error) instead of hanging the GPU.  The timer is only read every 4096 polls.
-__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-  const uint64_t t0 = globaltimer_ns();
+// Bounded wait: a barrier that has not completed after ~3e10 SM cycles (about 15 s) is a protocol bug — trap (the
+// launch fails with an error) instead of hanging the GPU.  clock64() is a single 64-bit SM-local counter; an earlier
+// version used %globaltimer with a 4 s limit and produced false time-outs (a torn 64-bit read at a 2^32 ns wrap of
+// the low word is off by 4.29 s).  The limit is checked twice before trapping.  Must stay inlined: kernels that
+// use setmaxnreg cannot contain real calls (ptxas would then cap every warp at the smallest register budget).
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
+  const long long t0 = clock64();
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++polls & 4095u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      printf("vats_attn: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
+    if ((++polls & 8191u) == 0 && clock64() - t0 > VATS_MBAR_TIMEOUT_CYCLES) {
+      if (clock64() - t0 > VATS_MBAR_TIMEOUT_CYCLES) {
+        unsigned long long state;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(state) : "r"(bar));
+        printf("vats_attn: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u tag 0x%x state 0x%llx)\n",
+               (int)blockIdx.x, (int)threadIdx.x, bar, parity, tag, state);
+        __trap();
+      }
     }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  mbar_wait_slow(bar, parity, tag);
 }
 
 // generic-proxy writes -> visible to the async proxy (TMA / UMMA reading smem)

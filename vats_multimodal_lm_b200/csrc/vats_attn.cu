@@ -11,10 +11,12 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 
 #include "decode.cuh"
+#include "decode_mma.cuh"
 #include "mask.cuh"
 #include "prefill_simt.cuh"
 #include "prefill_tc.cuh"
@@ -92,7 +94,8 @@ LoadMode plan_load(const void* ptr, int hd, const int64_t s[3]) {
   return ldg ? LoadMode::kLdg : LoadMode::kNone;
 }
 
-int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3]) {
+int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3],
+               int box_rows = 128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)heads, (cuuint64_t)T, (cuuint64_t)N};
@@ -101,7 +104,7 @@ int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int h
   if (heads == 1 || strides[0] == 0) strides[0] = (cuuint64_t)((hd + 7) / 8 * 8) * 2;
   if (T == 1 || strides[1] == 0) strides[1] = strides[0] * (cuuint64_t)heads;
   if (N == 1 || strides[2] == 0) strides[2] = strides[1] * (cuuint64_t)T;
-  const cuuint32_t box[4] = {64, 1, 128, 1};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -322,6 +325,103 @@ int decode_chunk_and_splits(int S_max, int left, int* chunk, int* splits) {
   return 0;
 }
 
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;  // B200; also the answer on a box without a GPU (workspace sizing must not fail there)
+  }
+  return sms;
+}
+
+// Split-K plan of the TMA + mma.sync decode kernel: enough items for ~20 per SM (static round-robin tail <= 5 %),
+// chunks are multiples of the 32-key stage.
+void decode_mma_plan(int B, int G, int hpg, int S_max, int left, int* hpg_tile, int* head_batches, int* chunk,
+                     int* splits) {
+  long long window = S_max;
+  if (left >= 0 && (long long)left + 1 < window) window = (long long)left + 1;
+  if (window < 1) window = 1;
+  *hpg_tile = hpg < vats::kDmMaxHeads ? hpg : vats::kDmMaxHeads;
+  *head_batches = (hpg + *hpg_tile - 1) / *hpg_tile;
+  const long long units = (long long)B * G * (*head_batches);
+  // Items are walked round-robin by one persistent CTA per SM: pick the split count whose last wave is fullest,
+  // charging ~0.4 % per extra split for its merge / partial traffic.  Splits never go below 64 keys.
+  const long long sms = sm_count();
+  long long max_ns = (window + 63) / 64;
+  if (max_ns > 64) max_ns = 64;
+  if (max_ns < 1) max_ns = 1;
+  long long want = 1;
+  double best = -1.0;
+  for (long long ns = 1; ns <= max_ns; ++ns) {
+    const long long items = units * ns;
+    const long long waves = (items + sms - 1) / sms;
+    const double eff = (double)items / (double)(waves * sms) - 0.004 * (double)ns;
+    if (eff > best + 1e-9) {
+      best = eff;
+      want = ns;
+    }
+  }
+  long long ch = (window + want - 1) / want;
+  ch = (ch + vats::kDmChunkAlign - 1) / vats::kDmChunkAlign * vats::kDmChunkAlign;
+  *chunk = (int)ch;
+  *splits = (int)((window + ch - 1) / ch);
+}
+
+size_t decode_mma_ws_bytes(int B, int H, int G, int hd, int S_max, int left) {
+  int tile, hb, chunk, ns;
+  decode_mma_plan(B, G, H / G, S_max, left, &tile, &hb, &chunk, &ns);
+  const size_t counters = ((size_t)B * G * hb * sizeof(int) + 255) / 256 * 256;
+  return counters + (ns > 1 ? (size_t)B * H * ns * ((size_t)hd + 2) * sizeof(float) : 0);
+}
+
+template <int HD, int NCW, int SK>
+int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+  // ring depth: as deep as the 227 KB of shared memory allow (bytes in flight are what hides the HBM latency)
+  int stages = 48;
+  while (vats::decode_mma_smem_bytes<HD, NCW, SK>(stages) > 227 * 1024 && stages > 2) --stages;
+  if (const char* e = getenv("VATS_DECODE_STAGES")) {  // tuning / debugging knob
+    const int want = atoi(e);
+    if (want >= 2 && want < stages) stages = want;
+  }
+  // The ring depth MUST be a multiple of the consumer-warp count, so that a slot is always consumed by the same
+  // warp: a consumer waits on a slot's "full" barrier by phase parity, which is only sound if it has itself seen
+  // the slot's previous phase complete (TMA completions of different slots are not ordered).
+  stages -= stages % NCW;
+  if (stages < NCW) return fail(VATS_ERR_UNSUPPORTED, "decode: shared memory too small for the stage ring");
+  const size_t smem = vats::decode_mma_smem_bytes<HD, NCW, SK>(stages);
+  P.stages = stages;
+  static thread_local size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(vats::decode_mma_kernel<HD, NCW, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    smem_set = smem;
+  }
+  int grid = sm_count();
+  if (grid > P.num_items) grid = P.num_items;
+  vats::decode_mma_kernel<HD, NCW, SK><<<grid, (NCW + 1) * 32, smem, st>>>(P, mk, mv);
+  CUDA_TRY(cudaGetLastError());
+  return VATS_OK;
+}
+
+// Consumer-warp count / stage size of the mma decode kernel: (4 warps, 32-key stages) or (8 warps, 16-key stages).
+int decode_mma_ncw() {
+  static int ncw = 0;
+  if (ncw == 0) {
+    const char* e = getenv("VATS_DECODE_CONSUMER_WARPS");  // tuning knob
+    ncw = (e && atoi(e) == 8) ? 8 : 4;  // measured on B200: 4 warps x 32-key stages 198 us, 8 x 16-key 279 us (cfg2)
+  }
+  return ncw;
+}
+int decode_mma_stage_keys() { return decode_mma_ncw() == 8 ? 16 : 32; }
+
+template <int HD>
+int launch_decode_mma_ncw(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+  return decode_mma_ncw() == 8 ? launch_decode_mma<HD, 8, 16>(P, mk, mv, st)
+                               : launch_decode_mma<HD, 4, 32>(P, mk, mv, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -361,10 +461,12 @@ int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd, const in
 size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left) {
   (void)G;
   if (B <= 0 || H <= 0 || hd <= 0 || S_max <= 0) return 0;
+  if (G <= 0 || H % G != 0) return 0;
   int chunk, splits;
   decode_chunk_and_splits(S_max, left, &chunk, &splits);
-  if (splits <= 1) return 16;
-  return (size_t)B * H * splits * ((size_t)hd + 2) * sizeof(float);
+  const size_t simt = splits <= 1 ? 16 : (size_t)B * H * splits * ((size_t)hd + 2) * sizeof(float);
+  const size_t mma = decode_mma_ws_bytes(B, H, G, hd, S_max, left);
+  return simt > mma ? simt : mma;
 }
 
 int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, void* o, const int32_t* seq_lens,
@@ -411,6 +513,45 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
       return fail(VATS_ERR_WORKSPACE, "decode workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
     p.ws_acc = reinterpret_cast<float*>(workspace);
     p.ws_ml = p.ws_acc + (size_t)B * H * p.num_splits * hd;
+  }
+
+  // ---- fast path: TMA-addressable cache (16-byte aligned base / strides, head_dim multiple of 16 up to 128)
+  {
+    const bool tma_ok = (hd == 16 || hd == 32 || hd == 64 || hd == 128) && S_max > 0 &&
+                        (reinterpret_cast<uintptr_t>(k_cache) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(v_cache) & 15u) == 0 && k_strides[0] % 8 == 0 &&
+                        k_strides[1] % 8 == 0 && k_strides[2] % 8 == 0 && v_strides[0] % 8 == 0 &&
+                        v_strides[1] % 8 == 0 && v_strides[2] % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(q) & 3u) == 0 && q_strides[0] % 2 == 0 && q_strides[1] % 2 == 0 &&
+                        (long long)B * G <= 0x3fffffffLL;
+    if (tma_ok) {
+      vats::DecodeMmaParams P;
+      std::memset(&P, 0, sizeof(P));
+      P.d = p;
+      decode_mma_plan(B, G, p.hpg, S_max, left, &P.hpg_tile, &P.d.head_batches, &P.d.chunk, &P.d.num_splits);
+      const size_t need = decode_mma_ws_bytes(B, H, G, hd, S_max, left);
+      if (!workspace || workspace_bytes < need)
+        return fail(VATS_ERR_WORKSPACE, "decode workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+      const size_t counters = ((size_t)B * G * P.d.head_batches * sizeof(int) + 255) / 256 * 256;
+      P.counters = reinterpret_cast<int*>(workspace);
+      P.d.ws_acc = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + counters);
+      P.d.ws_ml = P.d.ws_acc + (size_t)B * H * P.d.num_splits * hd;
+      const long long items = (long long)B * G * P.d.head_batches * P.d.num_splits;
+      if (items > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "decode: too many work items");
+      P.num_items = (int)items;
+      CUtensorMap mk, mv;
+      if ((rc = encode_map(&mk, k_cache, B, S_max, G, hd, k_strides, decode_mma_stage_keys())) != VATS_OK) return rc;
+      if ((rc = encode_map(&mv, v_cache, B, S_max, G, hd, v_strides, decode_mma_stage_keys())) != VATS_OK) return rc;
+      switch (hd) {
+        case 16: rc = launch_decode_mma_ncw<16>(P, mk, mv, st); break;
+        case 32: rc = launch_decode_mma_ncw<32>(P, mk, mv, st); break;
+        case 64: rc = launch_decode_mma_ncw<64>(P, mk, mv, st); break;
+        default: rc = launch_decode_mma_ncw<128>(P, mk, mv, st); break;
+      }
+      if (rc != VATS_OK) return rc;
+      g_launches = 1;
+      return VATS_OK;
+    }
   }
 
   // vector width: limited by head_dim, base alignment and strides of q, k and v

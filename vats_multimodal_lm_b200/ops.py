@@ -88,6 +88,24 @@ def _(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
     return q.new_empty(q.shape, dtype=torch.bfloat16)
 
 
+_DECODE_WS = {}
+
+
+def _decode_workspace(device, stream: int, B: int, H: int, G: int, hd: int, S_max: int, left: int) -> torch.Tensor:
+    """Split-K scratch for the decode kernels.  The C-ABI wants it zero-filled before its first use (the kernel's
+    split counters live there and are left at zero on return), so it is created once per (device, stream, geometry)
+    with torch.zeros and reused; calls sharing one workspace are ordered by their stream."""
+    key = (device.index, stream, B, H, G, hd, S_max, left)
+    ws = _DECODE_WS.get(key)
+    if ws is None:
+        if len(_DECODE_WS) > 64:
+            _DECODE_WS.clear()
+        nbytes = max(_ffi.decode_workspace_bytes(B, H, G, hd, S_max, left), 16)
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _DECODE_WS[key] = ws
+    return ws
+
+
 @torch.library.custom_op("vats::gqa_swa_decode", mutates_args=(), device_types="cuda")
 def gqa_swa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_lens: torch.Tensor,
                    scale: float, left: int) -> torch.Tensor:
@@ -112,10 +130,9 @@ def gqa_swa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor
     o = torch.empty((B, H, hd), dtype=torch.bfloat16, device=q.device)
     if o.numel() == 0:
         return o
-    ws_bytes = _ffi.decode_workspace_bytes(B, H, G, hd, S_max, left)
-    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
         stream = torch.cuda.current_stream().cuda_stream
+        ws = _decode_workspace(q.device, stream, B, H, G, hd, S_max, left)
         _ffi.decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), o.data_ptr(), seq_lens.data_ptr(),
                     B, H, G, hd, S_max, q.stride()[:2], k_cache.stride()[:3], v_cache.stride()[:3], o.stride()[:2],
                     scale, left, ws.data_ptr(), ws.numel(), stream)
