@@ -1,0 +1,12 @@
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+r = d["roofline"]
+print(f"decode: value={d['value']:.0f} GB/s achieved={r['achieved']:.0f} ({100*r['frac']:.1f}% of measured) launch_ms mean={r['launch_ms_mean']:.4f} min={r['launch_ms_min']:.4f} e2e={d['e2e']['value']:.0f} launches={d['gpu_launches']}")
+for k, v in d.get("other_workloads", {}).items():
+    if "error" in v:
+        print(k, "ERROR", v["error"]); continue
+    rf = v["roofline"]
+    extra = f" +allgather {v['ms_compute_plus_allgather']:.3f} ms" if "ms_compute_plus_allgather" in v else ""
+    print(f"{k:26s} {v['ms_compute']:.4f} ms  {v['tflops']:8.1f} TFLOP/s {v['gbs']:8.1f} GB/s  {rf['bound']} frac={100*rf['frac']:.1f}%{extra}")
+if d.get("cpu_baseline"): print("cpu_baseline", d["cpu_baseline"])
+print("clocks", d.get("clocks"))

@@ -61,12 +61,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // version used %globaltimer with a 4 s limit and produced false time-outs (a torn 64-bit read at a 2^32 ns wrap of
 // the low word is off by 4.29 s).  The limit is checked twice before trapping.  Must stay inlined: kernels that
 // use setmaxnreg cannot contain real calls (ptxas would then cap every warp at the smallest register budget).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ long long clock64_volatile() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
-  const long long t0 = clock64();
+  // the hardware parks the thread for up to the hint (ns) per poll, so waiting warps leave the issue slots to
+  // the warps that work; the clock is only read once every 1024 polls
+  long long t0 = 0;
   uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++polls & 8191u) == 0 && clock64() - t0 > VATS_MBAR_TIMEOUT_CYCLES) {
-      if (clock64() - t0 > VATS_MBAR_TIMEOUT_CYCLES) {
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64_volatile();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > VATS_MBAR_TIMEOUT_CYCLES) {
         unsigned long long state;
         asm volatile("ld.shared.b64 %0, [%1];" : "=l"(state) : "r"(bar));
         printf("vats_attn: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u tag 0x%x state 0x%llx)\n",
@@ -166,6 +189,42 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)1 << 46;                              // [46,48) descriptor version = 1 (Blackwell)
   d |= (uint64_t)2 << 61;                              // [61,64) layout = SWIZZLE_128B
   return d;
+}
+
+// Same MMAs with the 64-bit shared-memory descriptors passed as (lo, hi) halves: the issuing thread keeps `hi`
+// (LBO/SBO/version/swizzle) constant and only bumps `lo` (the 16-byte-granular start address) between K-steps.
+__device__ __forceinline__ void mma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
 
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.

@@ -221,6 +221,14 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1
                   : 0;
+  {
+    static int exp_poly = -1;
+    if (exp_poly < 0) {
+      const char* e = getenv("VATS_PREFILL_EXP_POLY");  // tuning knob
+      exp_poly = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    P.exp_poly = exp_poly;
+  }
   // ring depths: fill the 227 KB of shared memory (also pins one CTA per SM, which owns all 512 TMEM columns)
   const int tile_bytes = P.regions * vats::kTcRegionBytes;
   int stages = (int)((227 * 1024 - 1024 - (int)sizeof(vats::TcSmemBarriers) - 2 * tile_bytes) / tile_bytes);
