@@ -316,7 +316,7 @@ def bench_decode(args, world, peaks):
     )
 
 
-def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool):
+def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool, layout: str = "dense"):
     """One prefill-class workload. With shard=True the N sequences (x KV groups) are split over the ranks and the
     outputs all-gathered (cfg5 / ViT); returns per-rank-max timings."""
     from vats_multimodal_lm_b200 import ops, sharding
@@ -328,6 +328,11 @@ def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool):
     q = gen_unit_bf16((nb, T, ng * hpg, hd), 1234 + rank, dev, True)
     k = gen_unit_bf16((nb, T, ng, hd), 2234 + rank, dev, True)
     v = gen_unit_bf16((nb, T, ng, hd), 3234 + rank, dev, False)
+    if layout == "module" and hd % 8 != 0:
+        # the layout the drop-in modules produce for head dims TMA cannot address (modules/_common.py): same logical
+        # [N,T,heads,hd] tensors, head stride rounded up to 8 elements
+        from vats_multimodal_lm_b200.modules._common import _to_kernel_layout
+        q, k, v = _to_kernel_layout(q), _to_kernel_layout(k), _to_kernel_layout(v)
     scale = hd ** -0.5
     step = lambda: ops.gqa_swa_prefill(q, k, v, None, None, scale, c["causal"], c["left"], 0 if c["causal"] else -1, 0)
     flush = None
@@ -415,6 +420,12 @@ def run_ours(args):
             try:
                 other[c["name"]] = bench_prefill_cfg(c, peaks, steps, 3, world, rank, shard)
                 other[c["name"]]["sharded"] = shard
+                other[c["name"]]["layout"] = "dense [N,T,heads,hd]"
+                if c["hd"] % 8 != 0:
+                    r2 = bench_prefill_cfg(c, peaks, steps, 3, world, rank, shard, layout="module")
+                    r2["sharded"] = shard
+                    r2["layout"] = "as produced by the drop-in modules: head stride padded to 8 elements (TMA-addressable)"
+                    other[c["name"] + "_module_layout"] = r2
             except Exception as e:  # a secondary workload must not take the headline down
                 other[c["name"]] = {"error": f"{type(e).__name__}: {e}"}
     cpu = None

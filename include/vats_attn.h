@@ -136,6 +136,10 @@ int vats_attn_debug_tile_range(int q0, int block_m, int block_n, int Tq, int Tk,
 int vats_attn_debug_tile_is_full(int tile, int q0, int block_m, int block_n, int Tq, int Tk,
                                  int causal, int left, int right);
 
+/* Debug only: block 0 of the tensor-core prefill kernel appends (tag, SM clock) records to this device buffer of
+ * 4 roles x capacity x {tag, clock} uint64 records (zero it first); NULL switches tracing off. */
+void vats_attn_debug_set_trace(void* dev_buf, int capacity);
+
 const char* vats_attn_last_error(void);
 int vats_attn_version(void);
 

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "vats_attn_debug_mask",
     "vats_attn_debug_tile_range",
     "vats_attn_debug_tile_is_full",
+    "vats_attn_debug_set_trace",
     "vats_attn_last_error",
     "vats_attn_version",
 )
@@ -83,6 +84,8 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_debug_tile_range.argtypes = [i, i, i, i, i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(i)]
         lib.vats_attn_debug_tile_is_full.restype = i
         lib.vats_attn_debug_tile_is_full.argtypes = [i, i, i, i, i, i, i, i, i]
+        lib.vats_attn_debug_set_trace.restype = None
+        lib.vats_attn_debug_set_trace.argtypes = [vp, i]
         lib.vats_attn_last_error.restype = ctypes.c_char_p
         lib.vats_attn_last_error.argtypes = []
         lib.vats_attn_version.restype = i

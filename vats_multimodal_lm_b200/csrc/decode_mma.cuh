@@ -6,8 +6,9 @@
 // The kernel is a byte pump: decode is 4 flop/byte, so everything is organised around keeping >= 128 KB of K/V in
 // flight per SM and spending almost no issue slots per byte.
 //   * persistent CTAs (one per SM) walk a static list of work items (sequence b, KV group g, head batch, split);
-//   * the last warp is the producer (one elected lane): per stage of SK keys it issues the TMA boxes of K and V
-//     (128B-swizzled) into an mbarrier ring that runs across item boundaries — the ring never drains between items;
+//   * warps NCW..2NCW-1 are producers (one elected lane each, producer p feeds consumer p): per stage of SK keys
+//     they issue the TMA boxes of K and V (128B-swizzled) into an mbarrier ring that runs across item boundaries —
+//     the ring never drains between items;
 //   * warps 0-3 are consumers; stage i belongs to warp i % 4 and the ring depth is a multiple of 4, so a slot is
 //     always consumed by the same warp (required: a consumer waits on a slot by phase parity, which is only sound
 //     if it saw the slot's previous phase complete itself — TMA completions of different slots are unordered) and
@@ -90,7 +91,7 @@ __device__ __forceinline__ DmItem dm_decode_item(const DecodeMmaParams& P, int i
 
 // HD: head dim (multiple of 16, <= 128).  Shared memory: [stages][K halves | V halves][32 keys][128 B] + merge scratch.
 template <int HD, int NCW, int SK>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1)
+__global__ void __launch_bounds__(2 * NCW * 32, 1)
 decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v) {
   using namespace ptx;
@@ -127,28 +128,35 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
   }
   __syncthreads();
 
-  if (warp == kDmConsumerWarps) {
-    // =================================================================== producer (one elected lane)
+  if (warp >= kDmConsumerWarps) {
+    // =================================================================== producers: warp NCW + p feeds consumer p.
+    // One issuing thread needs ~300 cycles per TMA box (expect_tx, descriptor moves, barrier wait; measured with
+    // tools/micro/tma_bw.cu), far less than the TMA unit can take: one producer per consumer keeps the HBM stream
+    // full.  Ring slots / phases advance incrementally — an integer division costs this thread ~125 cycles.
+    const int pw = warp - kDmConsumerWarps;
     if (lane == 0) {
       prefetch_tmap(&tmap_k);
       prefetch_tmap(&tmap_v);
-      int gs = 0;  // global stage counter of this CTA
+      int slot = pw;        // slot of this producer's next stage (stages % NCW == 0: slot == pw mod NCW always)
+      uint32_t ph = 0u;     // its phase parity
+      int gs_mod = 0;       // (global stage index of the item's first stage) mod NCW
       for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
         const DmItem it = dm_decode_item<SK>(P, item);
-        for (int j = 0; j < it.nst; ++j, ++gs) {
-          const int s = gs % P.stages;
-          const uint32_t ph = (uint32_t)(gs / P.stages) & 1u;
-          mbar_wait(smem_u32(&empty[s]), ph ^ 1u, 0x10000000u | (uint32_t)gs);
-          const uint32_t bar = smem_u32(&full[s]);
+        for (int j = (pw - gs_mod) & (kDmConsumerWarps - 1); j < it.nst; j += kDmConsumerWarps) {
+          mbar_wait(smem_u32(&empty[slot]), ph ^ 1u, 0x10000000u | (uint32_t)j);
+          const uint32_t bar = smem_u32(&full[slot]);
           mbar_expect_tx(bar, STAGE_BYTES);
-          const uint32_t dst = ring + (uint32_t)s * STAGE_BYTES;
+          const uint32_t dst = ring + (uint32_t)slot * STAGE_BYTES;
           const int k0 = it.ks + j * SK;
 #pragma unroll
           for (int h = 0; h < HALVES; ++h) {
             tma_load_4d(dst + h * HALF_BYTES, &tmap_k, bar, 64 * h, it.g, k0, it.b);
             tma_load_4d(dst + TILE_BYTES + h * HALF_BYTES, &tmap_v, bar, 64 * h, it.g, k0, it.b);
           }
+          slot += kDmConsumerWarps;
+          if (slot >= P.stages) { slot -= P.stages; ph ^= 1u; }
         }
+        gs_mod = (gs_mod + it.nst) & (kDmConsumerWarps - 1);
       }
     }
     return;
@@ -157,7 +165,9 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
   // ===================================================================== consumers
   const int quad = lane >> 2;   // MMA row of c0/c1 == query head within the item
   const int qlane = lane & 3;
-  int gs_base = 0;
+  int slot = warp;      // ring slot of this warp's next stage
+  uint32_t cph = 0u;    // its phase parity
+  int gs_mod = 0;       // (global stage index of the item's first stage) mod NCW
 
   for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
     const DmItem it = dm_decode_item<SK>(P, item);
@@ -185,11 +195,11 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
     float m_run = -INFINITY;  // scaled-log2 units, row `quad`
     float l_run = 0.f;        // this thread's share of the row sum (quad-reduced at the end of the item)
 
-    for (int j = 0; j < it.nst; ++j) {
-      const int gs = gs_base + j;
-      if ((gs % kDmConsumerWarps) != warp) continue;
-      const int s = gs % P.stages;
-      mbar_wait(smem_u32(&full[s]), (uint32_t)(gs / P.stages) & 1u, 0x20000000u | (uint32_t)gs);
+    for (int j = (warp - gs_mod) & (kDmConsumerWarps - 1); j < it.nst; j += kDmConsumerWarps) {
+      const int s = slot;
+      mbar_wait(smem_u32(&full[s]), cph, 0x20000000u | (uint32_t)j);
+      slot += kDmConsumerWarps;
+      if (slot >= P.stages) { slot -= P.stages; cph ^= 1u; }
       const uint32_t kt = ring + (uint32_t)s * STAGE_BYTES;
       const uint32_t vt = kt + TILE_BYTES;
       const int kcount = min(SK, it.nkeys - j * SK);
@@ -308,7 +318,7 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
     }
-    gs_base += it.nst;
+    gs_mod = (gs_mod + it.nst) & (kDmConsumerWarps - 1);
 
     // ---- merge the four warps' (m, l, O) for this item through shared memory
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);

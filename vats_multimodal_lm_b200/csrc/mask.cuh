@@ -73,8 +73,10 @@ VATS_HD void tile_range(const MaskParams& p, int q0, int block_m, int block_n, i
     *last = -1;
     return;
   }
-  *first = (int)(lo / block_n);
-  *last = (int)(hi / block_n);
+  // lo, hi are inside [0, Tk) here: 32-bit division (a shift when block_n is a compile-time power of two; a 64-bit
+  // division costs a GPU thread hundreds of cycles)
+  *first = (int)lo / block_n;
+  *last = (int)hi / block_n;
 }
 
 // True when every (row, key) of the block × tile rectangle is allowed by the geometry and lies inside [0,Tk):

@@ -5,13 +5,14 @@
 // vit_3d/optimized_attention.py:185-348, with the window semantics of the (dead) FA2 call at
 // src/optimized_attention.py:628-635, and `extend_kv_heads` (utils/attention_utils.py:7-27) folded into indexing.
 //
-// One CTA owns one KV group g of one sequence n, one block of 128 query tokens, and a PAIR of query heads of that
+// Persistent CTAs (one per SM) walk the work items round-robin.  One item = one KV group g of one sequence n, one
+// block of 128 query tokens, and a PAIR of query heads of that
 // group (M-tile 0 and M-tile 1, 128 rows each).  Both tiles consume the same K/V tiles from shared memory
 // (GQA head-group reuse) and ping-pong on the tensor core so the softmax of one overlaps the MMAs of the other.
 //
 //   warps 0-3   softmax warpgroup of tile 0: thread r owns S row r (TMEM lane r) — row max / row sum are in-thread
 //   warps 4-7   softmax warpgroup of tile 1
-//   warp  8     TMA producer: Q tiles once, then K_j, V_j into mbarrier-guarded rings (128B-swizzled boxes)
+//   warps 8-10  TMA producers (one lane each): K ring, V ring, Q tiles — mbarrier-guarded, 128B-swizzled boxes
 //   warps 8-10  (only for head dims TMA cannot address, e.g. 60 or 66: rows are 4-byte, not 16-byte, aligned)
 //               LDG staging loaders: coalesced 32-bit loads, stored into the same 128B-swizzled layout
 //   warp  11    MMA issuer (one elected lane): S = Q·K^T (SS, both K-major), O += P·V (TS: P from TMEM, V MN-major)
@@ -46,6 +47,10 @@ struct TcParams {
   int nk, nv;        // ring depths
   int q_ldg, kv_ldg; // 1: the tensor is not TMA-addressable (row starts only 4-byte aligned): LDG staging instead
   int o_vec16;       // 1: O rows may be written with 16-byte stores
+  int num_work;      // N * G * pairs * q_blocks work items, walked round-robin by the persistent CTAs
+  unsigned div_qb[2], div_pairs[2], div_g[2];  // magic (multiplier, shift) pairs for division by q_blocks / pairs / G
+  unsigned long long* trace;  // debug: block 0 appends (tag, clock64) pairs here (NULL = off); [0] = count
+  int trace_cap;
   int exp_poly;      // 1: on unmasked tiles half of the exponentials run on the FMA pipe (degree-3 polynomial)
 };
 
@@ -54,9 +59,11 @@ struct TcSmemBarriers {
   uint64_t q_fixed[2];
   uint64_t k_full[kTcMaxStages], k_empty[kTcMaxStages];
   uint64_t v_full[kTcMaxStages], v_empty[kTcMaxStages];
+  uint64_t q_empty[2];   // the item's last S MMA has read Q tile t: the next item's Q may land
   uint64_t s_full[2];
   uint64_t p_full[2];
-  uint64_t o_full;
+  uint64_t o_full[2];
+  uint64_t o_empty[2];   // the softmax warpgroup has read O_t out of TMEM: the next item's P.V may overwrite it
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -118,6 +125,74 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Debug timeline: one thread per role of block 0 appends (tag, SM clock) records to its own lane of the buffer
+// (plain stores, no atomics, so the probe costs a few cycles): trace[role][i] = {tag, clock}, trace_cap records/role.
+struct TcTracer {
+  unsigned long long* base;
+  int n, cap;
+  __device__ __forceinline__ TcTracer(const TcParams& P, int role)
+      : base(P.trace != nullptr && blockIdx.x == 0 ? P.trace + (size_t)role * 2 * P.trace_cap : nullptr), n(0),
+        cap(P.trace_cap) {}
+  __device__ __forceinline__ void operator()(unsigned tag) {
+    if (base != nullptr && n < cap) {
+      base[2 * n] = tag;
+      base[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+};
+
+// One work item: (sequence n, KV group g, head pair, 128-token query block).
+struct TcWork {
+  int n, g, q0, head0;
+  int t_first, n_tiles;  // KV tile range (n_tiles <= 0: nothing to attend)
+  bool active1;          // the pair's second head exists
+};
+// n / d for n < 2^31 with a host-computed (multiplier, shift) pair — an integer division costs ~125 cycles on the
+// single-lane roles, and every role decodes every work item.
+__host__ __device__ __forceinline__ void tc_fastdiv(unsigned n, const unsigned (&magic)[2], unsigned d, unsigned* q,
+                                                    unsigned* r) {
+#if defined(__CUDA_ARCH__)
+  const unsigned quo = d != 1u ? __umulhi(n, magic[0]) >> magic[1] : n;
+#else
+  const unsigned quo = d != 1u ? (unsigned)(((unsigned long long)n * magic[0]) >> 32) >> magic[1] : n;
+#endif
+  *q = quo;
+  *r = n - quo * d;
+}
+inline void tc_find_divisor(unsigned d, unsigned (&magic)[2]) {
+  if (d <= 1u) {
+    magic[0] = 0u;
+    magic[1] = 0u;
+    return;
+  }
+  unsigned lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  magic[0] = (unsigned)(((1ull << p) + d - 1) / d);
+  magic[1] = p - 32;
+}
+
+__device__ __forceinline__ TcWork tc_decode_work(const TcParams& P, int w) {
+  const PrefillParams& a = P.a;
+  TcWork k;
+  unsigned rest, qbr, pair, g, n;
+  tc_fastdiv((unsigned)w, P.div_qb, (unsigned)P.q_blocks, &rest, &qbr);
+  const int qb = (P.q_blocks - 1) - (int)qbr;  // heavy (late) causal blocks first
+  tc_fastdiv(rest, P.div_pairs, (unsigned)P.pairs, &rest, &pair);
+  tc_fastdiv(rest, P.div_g, (unsigned)a.G, &n, &g);
+  k.g = (int)g;
+  k.n = (int)n;
+  k.q0 = qb * kTcBlockM;
+  const int hh0 = (int)pair * 2;
+  k.active1 = (hh0 + 1) < a.hpg;
+  k.head0 = k.g * a.hpg + hh0;
+  int t_last;
+  tile_range(a.mask, k.q0, kTcBlockM, kTcBlockN, &k.t_first, &t_last);
+  k.n_tiles = t_last - k.t_first + 1;
+  return k;
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v) {
@@ -135,23 +210,6 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
   TcSmemBarriers* bars =
       reinterpret_cast<TcSmemBarriers*>(smem_raw + (base - raw) + (size_t)(2 + P.nk + P.nv) * tile_bytes);
 
-  // ---- work decode: q block fastest, then (group, pair), then sequence
-  int bid = blockIdx.x;
-  const int qb = (P.q_blocks - 1) - (bid % P.q_blocks);  // heavy (late) causal blocks first
-  bid /= P.q_blocks;
-  const int pair = bid % P.pairs;
-  bid /= P.pairs;
-  const int g = bid % a.G;
-  const int n = bid / a.G;
-  const int q0 = qb * kTcBlockM;
-  const int hh0 = pair * 2;  // head-in-group of tile 0
-  const bool active1 = (hh0 + 1) < a.hpg;
-  const int head0 = g * a.hpg + hh0;
-
-  int t_first, t_last;
-  tile_range(a.mask, q0, kTcBlockM, kTcBlockN, &t_first, &t_last);
-  const int n_tiles = t_last - t_first + 1;  // <= 0: nothing to attend
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -163,8 +221,11 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->q_full[t]), 1);
       mbar_init(smem_u32(&bars->q_fixed[t]), 128);
+      mbar_init(smem_u32(&bars->q_empty[t]), 1);
       mbar_init(smem_u32(&bars->s_full[t]), 1);
       mbar_init(smem_u32(&bars->p_full[t]), 128);
+      mbar_init(smem_u32(&bars->o_full[t]), 1);
+      mbar_init(smem_u32(&bars->o_empty[t]), 128);
     }
     const uint32_t kv_arrivals = P.kv_ldg ? kTcLoaderThreads : 1;
     for (int s = 0; s < kTcMaxStages; ++s) {
@@ -173,7 +234,6 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->v_full[s]), kv_arrivals);
       mbar_init(smem_u32(&bars->v_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bars->o_full), 1);
     fence_mbar_init();
   }
   if (warp == 11) {
@@ -189,70 +249,96 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     // =========================================================== warpgroup 2: producers (warps 8-10) + MMA issuer (11)
     setmaxnreg_dec<80>();
   if (warp <= 10) {
-    if (warp == 8 && lane == 0 && n_tiles > 0 && !P.q_ldg) {
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1 && !active1) break;
-        const uint32_t bar = smem_u32(&bars->q_full[t]);
-        mbar_expect_tx(bar, tile_bytes);
-        for (int c = 0; c < P.regions; ++c)
-          tma_load_4d(sQ + t * tile_bytes + c * kTcRegionBytes, &tmap_q, bar, 64 * c, head0 + t, q0, n);
-      }
-    }
     if (!P.kv_ldg) {
-      // ---- TMA: one elected lane feeds the K and V rings
-      if (warp == 8 && lane == 0) {
-        for (int j = 0; j < n_tiles; ++j) {
-          const int k0 = (t_first + j) * kTcBlockN;
-          {
-            const int s = j % P.nk;
-            mbar_wait(smem_u32(&bars->k_empty[s]), ((uint32_t)(j / P.nk) & 1u) ^ 1u);
-            const uint32_t bar = smem_u32(&bars->k_full[s]);
-            mbar_expect_tx(bar, tile_bytes);
-            for (int c = 0; c < P.regions; ++c)
-              tma_load_4d(sK + s * tile_bytes + c * kTcRegionBytes, &tmap_k, bar, 64 * c, g, k0, n);
+      // ---- TMA: three issuing lanes — warp 8 feeds the K ring, warp 9 the V ring, warp 10 the Q tiles.  One thread
+      //      needs ~300 cycles per box (tools/micro/tma_bw.cu), so a single producer would serialise the 8 boxes an
+      //      item starts with; the rings run continuously across items.
+      if (lane == 0) {
+        TcTracer trace(P, 0);
+        if (warp == 10) {
+          if (!P.q_ldg) {
+            uint32_t qn[2] = {0u, 0u};      // items in which tile t took part so far
+            for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
+              const TcWork wk = tc_decode_work(P, w);
+              if (wk.n_tiles <= 0) continue;
+              for (int t = 0; t < 2; ++t) {
+                if (t == 1 && !wk.active1) break;
+                mbar_wait(smem_u32(&bars->q_empty[t]), (qn[t] & 1u) ^ 1u);
+                const uint32_t bar = smem_u32(&bars->q_full[t]);
+                mbar_expect_tx(bar, tile_bytes);
+                for (int c = 0; c < P.regions; ++c)
+                  tma_load_4d(sQ + t * tile_bytes + c * kTcRegionBytes, &tmap_q, bar, 64 * c, wk.head0 + t, wk.q0, wk.n);
+                ++qn[t];
+              }
+              trace(0x300);
+            }
           }
-          {
-            const int s = j % P.nv;
-            mbar_wait(smem_u32(&bars->v_empty[s]), ((uint32_t)(j / P.nv) & 1u) ^ 1u);
-            const uint32_t bar = smem_u32(&bars->v_full[s]);
-            mbar_expect_tx(bar, tile_bytes);
-            for (int c = 0; c < P.regions; ++c)
-              tma_load_4d(sV + s * tile_bytes + c * kTcRegionBytes, &tmap_v, bar, 64 * c, g, k0, n);
+        } else {
+          // warp 8: K, warp 9: V
+          const bool is_k = warp == 8;
+          const CUtensorMap* tmap = is_k ? &tmap_k : &tmap_v;
+          uint64_t* full = is_k ? bars->k_full : bars->v_full;
+          uint64_t* empty = is_k ? bars->k_empty : bars->v_empty;
+          const uint32_t ring = is_k ? sK : sV;
+          const int depth = is_k ? P.nk : P.nv;
+          int slot = 0;
+          uint32_t ph = 0u;
+          for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
+            const TcWork wk = tc_decode_work(P, w);
+            for (int j = 0; j < wk.n_tiles; ++j) {
+              const int k0 = (wk.t_first + j) * kTcBlockN;
+              mbar_wait(smem_u32(&empty[slot]), ph ^ 1u);
+              if (is_k) trace(0x310 + j);
+              const uint32_t bar = smem_u32(&full[slot]);
+              mbar_expect_tx(bar, tile_bytes);
+              for (int c = 0; c < P.regions; ++c)
+                tma_load_4d(ring + slot * tile_bytes + c * kTcRegionBytes, tmap, bar, 64 * c, wk.g, k0, wk.n);
+              if (++slot == depth) { slot = 0; ph ^= 1u; }
+            }
           }
         }
       }
     } else {
       // ---- LDG staging: 96 threads copy each K / V tile into the swizzled layout
       const int ltid = threadIdx.x - 8 * 32;
-      const __nv_bfloat16* kbase = a.k + n * a.ks_n + (long long)g * a.ks_h;
-      const __nv_bfloat16* vbase = a.v + n * a.vs_n + (long long)g * a.vs_h;
       unsigned char* sK_g = smem_raw + (sK - raw);
       unsigned char* sV_g = smem_raw + (sV - raw);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int k0 = (t_first + j) * kTcBlockN;
-        {
-          const int s = j % P.nk;
-          mbar_wait(smem_u32(&bars->k_empty[s]), ((uint32_t)(j / P.nk) & 1u) ^ 1u);
-          ldg_stage_tile<kTcLoaderThreads>(sK_g + (size_t)s * tile_bytes, kbase, a.ks_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
-          fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&bars->k_full[s]));
-        }
-        {
-          const int s = j % P.nv;
-          mbar_wait(smem_u32(&bars->v_empty[s]), ((uint32_t)(j / P.nv) & 1u) ^ 1u);
-          ldg_stage_tile<kTcLoaderThreads>(sV_g + (size_t)s * tile_bytes, vbase, a.vs_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
-          fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&bars->v_full[s]));
+      int ks = 0, vs = 0;
+      uint32_t kph = 0u, vph = 0u;
+      for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
+        const TcWork wk = tc_decode_work(P, w);
+        if (wk.n_tiles <= 0) continue;
+        const __nv_bfloat16* kbase = a.k + wk.n * a.ks_n + (long long)wk.g * a.ks_h;
+        const __nv_bfloat16* vbase = a.v + wk.n * a.vs_n + (long long)wk.g * a.vs_h;
+        for (int j = 0; j < wk.n_tiles; ++j) {
+          const int k0 = (wk.t_first + j) * kTcBlockN;
+          {
+            mbar_wait(smem_u32(&bars->k_empty[ks]), kph ^ 1u);
+            ldg_stage_tile<kTcLoaderThreads>(sK_g + (size_t)ks * tile_bytes, kbase, a.ks_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(&bars->k_full[ks]));
+            if (++ks == P.nk) { ks = 0; kph ^= 1u; }
+          }
+          {
+            mbar_wait(smem_u32(&bars->v_empty[vs]), vph ^ 1u);
+            ldg_stage_tile<kTcLoaderThreads>(sV_g + (size_t)vs * tile_bytes, vbase, a.vs_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(&bars->v_full[vs]));
+            if (++vs == P.nv) { vs = 0; vph ^= 1u; }
+          }
         }
       }
     }
   } else {
     // =========================================================== MMA issuer
-    if (lane == 0 && n_tiles > 0) {
+    {
+      // every lane runs this block; `leader` marks the one lane whose tcgen05 instructions take effect
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      TcTracer trace(P, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);  // tell the compiler it is warp-uniform
       const uint32_t idesc_s = make_idesc_bf16(kTcBlockM, kTcBlockN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(kTcBlockM, P.hd_pad, 0, 1);
       const int ksteps = P.hd_pad / 16;
-      const int ntile_heads = active1 ? 2 : 1;
 
       // The issuing thread is a single lane running a dependent instruction stream: every instruction costs ~5
       // cycles of latency, so the loop is kept to a handful of integer ops per MMA — descriptor high words are
@@ -264,7 +350,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       const uint32_t k_lo_base = smem_desc_lo(sK, 16);
       const uint32_t v_lo_base = smem_desc_lo(sV, kTcRegionBytes);
       const uint32_t tile_step = tile_bytes >> 4;        // descriptor units (16 B) per ring slot
-      const uint32_t tS0 = tmem, tS1 = tmem + 128, tO0 = tmem + 256, tO1 = tmem + 384;
+      const uint32_t tS0 = tmem_u, tS1 = tmem_u + 128, tO0 = tmem_u + 256, tO1 = tmem_u + 384;
 
       // K-step ks reads 32 bytes further along the 128-byte swizzled row; after 4 steps it moves to the next
       // 64-element region.  Offsets are in descriptor units (16 B).  (A fully unrolled variant with immediate
@@ -273,7 +359,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         constexpr uint32_t R = kTcRegionBytes >> 4;
         uint32_t acc = 0u;
         for (int ks = 0; ks < ksteps; ++ks) {
-          mma_ss_lohi(d_tmem, q_lo, hi_k, k_lo, hi_k, idesc_s, acc);
+          mma_ss_lohi(d_tmem, q_lo, hi_k, k_lo, hi_k, idesc_s, acc, leader);
           acc = 1u;
           const uint32_t step = ((ks & 3) == 3) ? (R - 6u) : 2u;
           q_lo += step;
@@ -283,63 +369,90 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       auto issue_pv = [&](uint32_t p_tmem, uint32_t v_lo, uint32_t d_tmem, uint32_t acc) {
 #pragma unroll
         for (int ks = 0; ks < kTcBlockN / 16; ++ks) {
-          mma_ts_lohi(d_tmem, p_tmem + ks * 8, v_lo + ks * (2048 >> 4), hi_v, idesc_o, acc);
+          mma_ts_lohi(d_tmem, p_tmem + ks * 8, v_lo + ks * (2048 >> 4), hi_v, idesc_o, acc, leader);
           acc = 1u;
         }
       };
 
-      for (int t = 0; t < ntile_heads; ++t) {
-        if (P.q_ldg) mbar_wait(smem_u32(&bars->q_fixed[t]), 0);
-        else mbar_wait(smem_u32(&bars->q_full[t]), 0);
-      }
-      mbar_wait(smem_u32(&bars->k_full[0]), 0);
-      tc_fence_after();
-      issue_s(q_lo0, k_lo_base, tS0);
-      tc_commit(smem_u32(&bars->s_full[0]));
-      if (active1) {
-        issue_s(q_lo1, k_lo_base, tS1);
-        tc_commit(smem_u32(&bars->s_full[1]));
-      }
-      tc_commit(smem_u32(&bars->k_empty[0]));
-
-      int ksn = (P.nk > 1) ? 1 : 0;          // ring slot of K_{j+1}
-      uint32_t kph = (P.nk > 1) ? 0u : 1u;   // its phase parity
-      int vs = 0;                            // ring slot of V_j
-      uint32_t vph = 0u;
+      int ks = 0, vs = 0;                 // ring slot of the next K tile / of the current V tile
+      uint32_t kph = 0u, vph = 0u;
+      uint32_t pc[2] = {0u, 0u};          // P phases consumed per tile (running across items)
+      uint32_t qn[2] = {0u, 0u};          // items in which tile t took part so far
       const uint32_t p_bar0 = smem_u32(&bars->p_full[0]), p_bar1 = smem_u32(&bars->p_full[1]);
       const uint32_t s_bar0 = smem_u32(&bars->s_full[0]), s_bar1 = smem_u32(&bars->s_full[1]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const bool has_next = (j + 1) < n_tiles;
-        const uint32_t jp = (uint32_t)j & 1u;
-        const uint32_t v_lo = v_lo_base + (uint32_t)vs * tile_step;
-        const uint32_t k_lo = k_lo_base + (uint32_t)ksn * tile_step;
-        mbar_wait(smem_u32(&bars->v_full[vs]), vph);
-        // ---- tile 0
-        mbar_wait(p_bar0, jp);
+      for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
+        const TcWork wk = tc_decode_work(P, w);
+        if (wk.n_tiles <= 0) continue;
+        const bool active1 = wk.active1;
+        const int n_tiles = wk.n_tiles;
+        // ---- Q tiles of this item, first K tile, S(0) for both heads
+        mbar_wait(smem_u32(P.q_ldg ? &bars->q_fixed[0] : &bars->q_full[0]), qn[0] & 1u);
+        if (active1) mbar_wait(smem_u32(P.q_ldg ? &bars->q_fixed[1] : &bars->q_full[1]), qn[1] & 1u);
+        if (leader) trace(0x100);
+        mbar_wait(smem_u32(&bars->k_full[ks]), kph);
+        if (leader) trace(0x101);
         tc_fence_after();
-        issue_pv(tS0, v_lo, tO0, j > 0 ? 1u : 0u);
-        if (has_next) {
-          mbar_wait(smem_u32(&bars->k_full[ksn]), kph);
-          tc_fence_after();
-          issue_s(q_lo0, k_lo, tS0);
-          tc_commit(s_bar0);
-        }
-        // ---- tile 1
+        issue_s(q_lo0, k_lo_base + (uint32_t)ks * tile_step, tS0);
+        tc_commit_pred(s_bar0, leader);
+        if (n_tiles == 1) tc_commit_pred(smem_u32(&bars->q_empty[0]), leader);
         if (active1) {
-          mbar_wait(p_bar1, jp);
+          issue_s(q_lo1, k_lo_base + (uint32_t)ks * tile_step, tS1);
+          tc_commit_pred(s_bar1, leader);
+          if (n_tiles == 1) tc_commit_pred(smem_u32(&bars->q_empty[1]), leader);
+        }
+        tc_commit_pred(smem_u32(&bars->k_empty[ks]), leader);
+        if (++ks == P.nk) { ks = 0; kph ^= 1u; }
+
+        for (int j = 0; j < n_tiles; ++j) {
+          const bool has_next = (j + 1) < n_tiles;
+          const bool last_s = (j + 2) == n_tiles;   // the S issued in this iteration is the item's last read of Q
+          const uint32_t v_lo = v_lo_base + (uint32_t)vs * tile_step;
+          const uint32_t k_lo = k_lo_base + (uint32_t)ks * tile_step;
+          mbar_wait(smem_u32(&bars->v_full[vs]), vph);
+          if (leader) trace(0x110 + j);
+          // ---- tile 0
+          mbar_wait(p_bar0, pc[0] & 1u);
+          if (leader) trace(0x120 + j);
+          ++pc[0];
+          if (j == 0) mbar_wait(smem_u32(&bars->o_empty[0]), (qn[0] & 1u) ^ 1u);  // previous item's O_0 was read out
           tc_fence_after();
-          issue_pv(tS1, v_lo, tO1, j > 0 ? 1u : 0u);
+          issue_pv(tS0, v_lo, tO0, j > 0 ? 1u : 0u);
           if (has_next) {
-            issue_s(q_lo1, k_lo, tS1);
-            tc_commit(s_bar1);
+            mbar_wait(smem_u32(&bars->k_full[ks]), kph);
+            tc_fence_after();
+            issue_s(q_lo0, k_lo, tS0);
+            tc_commit_pred(s_bar0, leader);
+            if (last_s) tc_commit_pred(smem_u32(&bars->q_empty[0]), leader);
+          }
+          // ---- tile 1
+          if (active1) {
+            mbar_wait(p_bar1, pc[1] & 1u);
+            if (leader) trace(0x130 + j);
+            ++pc[1];
+            if (j == 0) mbar_wait(smem_u32(&bars->o_empty[1]), (qn[1] & 1u) ^ 1u);
+            tc_fence_after();
+            issue_pv(tS1, v_lo, tO1, j > 0 ? 1u : 0u);
+            if (has_next) {
+              issue_s(q_lo1, k_lo, tS1);
+              tc_commit_pred(s_bar1, leader);
+              if (last_s) tc_commit_pred(smem_u32(&bars->q_empty[1]), leader);
+            }
+          }
+          tc_commit_pred(smem_u32(&bars->v_empty[vs]), leader);
+          if (++vs == P.nv) { vs = 0; vph ^= 1u; }
+          if (has_next) {
+            tc_commit_pred(smem_u32(&bars->k_empty[ks]), leader);
+            if (++ks == P.nk) { ks = 0; kph ^= 1u; }
           }
         }
-        tc_commit(smem_u32(&bars->v_empty[vs]));
-        if (has_next) tc_commit(smem_u32(&bars->k_empty[ksn]));
-        if (++vs == P.nv) { vs = 0; vph ^= 1u; }
-        if (++ksn == P.nk) { ksn = 0; kph ^= 1u; }
+        if (leader) trace(0x140);
+        tc_commit_pred(smem_u32(&bars->o_full[0]), leader);
+        ++qn[0];
+        if (active1) {
+          tc_commit_pred(smem_u32(&bars->o_full[1]), leader);
+          ++qn[1];
+        }
       }
-      tc_commit(smem_u32(&bars->o_full));
     }
   }
   } else {
@@ -347,19 +460,27 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     setmaxnreg_inc<208>();
     const int t = warp >> 2;
     const int r = threadIdx.x & 127;           // row within the tile == TMEM lane
-    const int tok = q0 + r;
-    const int head = head0 + t;
-    const bool tile_active = (t == 0) || active1;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_base + (uint32_t)t * 128;
     const uint32_t tO = tmem + lane_base + 256 + (uint32_t)t * 128;
+    TcTracer trace(P, 2 + t);
+    uint32_t sc = 0u;   // S phases consumed by this tile (running across items)
+    uint32_t qn = 0u;   // items in which this tile took part so far
+
+    for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
+    const TcWork wk = tc_decode_work(P, w);
+    const int n = wk.n, q0 = wk.q0, t_first = wk.t_first, n_tiles = wk.n_tiles;
+    const int tok = q0 + r;
+    const int head = wk.head0 + t;
+    const bool tile_active = (t == 0) || wk.active1;
 
     float l_run = 0.f;
     float m_used = -INFINITY;  // reference maximum in scaled-log2 units; -inf = not set yet
 
     if (tile_active && n_tiles > 0) {
       if (P.q_ldg) {
-        // the 128 threads of this warpgroup stage their own Q tile (once per CTA)
+        // the 128 threads of this warpgroup stage their own Q tile, once the previous item's MMAs are done with it
+        mbar_wait(smem_u32(&bars->q_empty[t]), (qn & 1u) ^ 1u);
         const __nv_bfloat16* qbase = a.q + n * a.qs_n + (long long)head * a.qs_h;
         ldg_stage_tile<128>(smem_raw + (sQ - raw) + (size_t)t * tile_bytes, qbase, a.qs_t, q0, a.Tq, a.hd, P.hd_pad, r);
         fence_proxy_async_smem();
@@ -369,7 +490,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       for (int j = 0; j < n_tiles; ++j) {
         const int tile = t_first + j;
         const int k0 = tile * kTcBlockN;
-        mbar_wait(smem_u32(&bars->s_full[t]), (uint32_t)j & 1u);
+        if (r == 0) trace(0x200 + j);
+        mbar_wait(smem_u32(&bars->s_full[t]), sc & 1u);
+        if (r == 0) trace(0x210 + j);
+        ++sc;
         tc_fence_after();
         uint32_t sr[128];
         tmem_ld_32x32b_x32(tS + 0, sr + 0);
@@ -490,12 +614,13 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[t]));
+        if (r == 0) trace(0x220 + j);
       }
     }
 
-    // ---- epilogue: O / l -> bf16 -> global
-    // (tcgen05.ld is warp-collective: every lane of an active tile's warps runs the loads; only the global
-    //  stores are predicated on the row being inside the sequence)
+    // ---- epilogue: O / l -> bf16 -> global.  The whole O row is pulled out of TMEM first and the accumulator is
+    //      handed back (o_empty) before the global stores, so the next item's MMAs overlap this item's write-out.
+    //      (tcgen05.ld is warp-collective: every lane runs the loads; only the stores are predicated on the row.)
     if (tile_active) {
       const bool do_store = tok < a.Tq;
       bool qok = true;
@@ -503,47 +628,67 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       const float inv = (qok && l_run > 0.f && n_tiles > 0) ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = a.o + n * a.os_n + (long long)tok * a.os_t + (long long)head * a.os_h;
       if (n_tiles > 0) {
-        mbar_wait(smem_u32(&bars->o_full), 0);
+        if (r == 0) trace(0x230);
+        mbar_wait(smem_u32(&bars->o_full[t]), qn & 1u);
+        if (r == 0) trace(0x231);
         tc_fence_after();
       }
-      for (int c = 0; c < P.hd_pad; c += 16) {
-        uint32_t orr[16];
-        if (n_tiles > 0) {
-          tmem_ld_32x32b_x16(tO + c, orr);
-          tmem_ld_wait();
-        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) orr[i] = 0u;
-        }
-        __syncwarp();
-        if (do_store) {
-        uint32_t w[8];
+      for (int qd = 0; qd < 4; ++qd) {        // 32 accumulator columns at a time (keeps the row out of local memory)
+        if (qd * 32 < P.hd_pad) {
+          uint32_t tmp[32];
+          if (n_tiles > 0) {
+            tmem_ld_32x32b_x16(tO + qd * 32, tmp);
+            if (qd * 32 + 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + qd * 32 + 16, tmp + 16);
+            tmem_ld_wait();
+            if (qd * 32 + 32 >= P.hd_pad) {   // last chunk is out of TMEM: hand the accumulator back before storing
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->o_empty[t]));
+              ++qn;
+            }
+          } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          w[i] = pack_bf16x2(__uint_as_float(orr[2 * i]) * inv, __uint_as_float(orr[2 * i + 1]) * inv);
-        if (P.o_vec16 && c + 16 <= a.hd) {
-          *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-        } else {
+            for (int i = 0; i < 32; ++i) tmp[i] = 0u;
+          }
+          if (do_store) {
+            uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int e = c + 2 * i;
-            if (e + 1 < a.hd) {
-              if ((reinterpret_cast<uintptr_t>(orow + e) & 3u) == 0) {
-                *reinterpret_cast<uint32_t*>(orow + e) = w[i];
-              } else {
-                reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(w[i] & 0xffffu);
-                reinterpret_cast<uint16_t*>(orow)[e + 1] = (uint16_t)(w[i] >> 16);
+            for (int i = 0; i < 16; ++i)
+              w[i] = pack_bf16x2(__uint_as_float(tmp[2 * i]) * inv, __uint_as_float(tmp[2 * i + 1]) * inv);
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              const int c = qd * 32 + hc * 16;
+              if (c < P.hd_pad) {
+                if (P.o_vec16 && c + 16 <= a.hd) {
+                  *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[hc * 8 + 0], w[hc * 8 + 1], w[hc * 8 + 2], w[hc * 8 + 3]);
+                  *reinterpret_cast<uint4*>(orow + c + 8) =
+                      make_uint4(w[hc * 8 + 4], w[hc * 8 + 5], w[hc * 8 + 6], w[hc * 8 + 7]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int e = c + 2 * i;
+                    const uint32_t wv = w[hc * 8 + i];
+                    if (e + 1 < a.hd) {
+                      if ((reinterpret_cast<uintptr_t>(orow + e) & 3u) == 0) {
+                        *reinterpret_cast<uint32_t*>(orow + e) = wv;
+                      } else {
+                        reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(wv & 0xffffu);
+                        reinterpret_cast<uint16_t*>(orow)[e + 1] = (uint16_t)(wv >> 16);
+                      }
+                    } else if (e < a.hd) {
+                      reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(wv & 0xffffu);
+                    }
+                  }
+                }
               }
-            } else if (e < a.hd) {
-              reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(w[i] & 0xffffu);
             }
           }
         }
-        }  // do_store
-        __syncwarp();
       }
+      __syncwarp();
+      if (r == 0) trace(0x240);
     }
+    }  // work items
   }
 
   // ---- teardown

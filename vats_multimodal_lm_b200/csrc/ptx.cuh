@@ -80,11 +80,11 @@ __device__ __forceinline__ long long clock64_volatile() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
-  // the hardware parks the thread for up to the hint (ns) per poll, so waiting warps leave the issue slots to
-  // the warps that work; the clock is only read once every 1024 polls
+  // plain try_wait polls (the default hardware suspend window); an explicit 2 us suspend-time hint was measured to
+  // add micro-seconds to every dependency edge (warps showed up as "sleeping").  The clock is read every 1024 polls.
   long long t0 = 0;
   uint32_t polls = 0;
-  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+  while (!mbar_try_wait(bar, parity)) {
     if ((++polls & 1023u) == 0) {
       const long long now = clock64_volatile();
       if (t0 == 0) {
@@ -193,31 +193,45 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 
 // Same MMAs with the 64-bit shared-memory descriptors passed as (lo, hi) halves: the issuing thread keeps `hi`
 // (LBO/SBO/version/swizzle) constant and only bumps `lo` (the 16-byte-granular start address) between K-steps.
+// The whole issuing warp executes these (convergent control flow, warp-uniform operands, so the compiler keeps the
+// descriptors in uniform registers instead of moving them there per instruction); only the elected lane (`leader`
+// != 0) actually issues.
 __device__ __forceinline__ void mma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t accumulate) {
+                                            uint32_t idesc, uint32_t accumulate, uint32_t leader) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, pl;\n\t"
       ".reg .b64 da, db;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "setp.ne.b32 pl, %7, 0;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ void mma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t accumulate) {
+                                            uint32_t idesc, uint32_t accumulate, uint32_t leader) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, pl;\n\t"
       ".reg .b64 db;\n\t"
       "mov.b64 db, {%2, %3};\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "setp.ne.b32 pl, %6, 0;\n\t"
+      "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pl;\n\t"
+      "setp.ne.b32 pl, %1, 0;\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar), "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -25,6 +25,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
+unsigned long long* g_trace = nullptr;  // debug timeline buffer (device memory), see vats_attn_debug_set_trace
+int g_trace_cap = 0;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -116,6 +118,17 @@ int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int h
                 (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
                 (unsigned long long)strides[2]);
   return VATS_OK;
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;  // B200; also the answer on a box without a GPU (workspace sizing must not fail there)
+  }
+  return sms;
 }
 
 struct PrefillArgs {
@@ -215,8 +228,10 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.regions = (P.hd_pad + 63) / 64;
   P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
   P.pairs = (P.a.hpg + 1) / 2;
-  P.q_ldg = pl.q == LoadMode::kLdg ? 1 : 0;
-  P.kv_ldg = (pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg) ? 1 : 0;
+  // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
+  const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  P.q_ldg = any_ldg ? 1 : 0;
+  P.kv_ldg = any_ldg ? 1 : 0;
   P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1
@@ -258,7 +273,15 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  vats::prefill_tc_kernel<<<(unsigned)ctas, vats::kTcThreads, smem, st>>>(P, mq, mk, mv);
+  P.num_work = (int)ctas;
+  vats::tc_find_divisor((unsigned)P.q_blocks, P.div_qb);
+  vats::tc_find_divisor((unsigned)P.pairs, P.div_pairs);
+  vats::tc_find_divisor((unsigned)A.G, P.div_g);
+  P.trace = g_trace;
+  P.trace_cap = g_trace_cap;
+  int grid = sm_count();
+  if (grid > P.num_work) grid = P.num_work;
+  vats::prefill_tc_kernel<<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
   return VATS_OK;
@@ -333,16 +356,6 @@ int decode_chunk_and_splits(int S_max, int left, int* chunk, int* splits) {
   return 0;
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;  // B200; also the answer on a box without a GPU (workspace sizing must not fail there)
-  }
-  return sms;
-}
 
 // Split-K plan of the TMA + mma.sync decode kernel: enough items for ~20 per SM (static round-robin tail <= 5 %),
 // chunks are multiples of the 32-key stage.
@@ -408,7 +421,7 @@ int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUt
   }
   int grid = sm_count();
   if (grid > P.num_items) grid = P.num_items;
-  vats::decode_mma_kernel<HD, NCW, SK><<<grid, (NCW + 1) * 32, smem, st>>>(P, mk, mv);
+  vats::decode_mma_kernel<HD, NCW, SK><<<grid, 2 * NCW * 32, smem, st>>>(P, mk, mv);
   CUDA_TRY(cudaGetLastError());
   return VATS_OK;
 }
@@ -435,6 +448,10 @@ int launch_decode_mma_ncw(vats::DecodeMmaParams& P, const CUtensorMap& mk, const
 extern "C" {
 
 int vats_attn_version(void) { return VATS_ATTN_VERSION; }
+void vats_attn_debug_set_trace(void* dev_buf, int capacity) {
+  g_trace = reinterpret_cast<unsigned long long*>(dev_buf);
+  g_trace_cap = capacity;
+}
 const char* vats_attn_last_error(void) { return g_err; }
 int vats_attn_last_launch_count(void) { return g_launches; }
 

@@ -57,6 +57,24 @@ def apply_qk_norm(query: torch.Tensor, key: torch.Tensor) -> Tuple[torch.Tensor,
     return F.normalize(query, p=2, dim=-1, eps=1e-6), F.normalize(key, p=2, dim=-1, eps=1e-6)
 
 
+def _to_kernel_layout(x: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a [N, T, heads, hd] tensor in a TMA-addressable layout.
+
+    The cast to bf16 writes a new tensor anyway; for head dims that are not a multiple of 8 (60, 66) it is written
+    into a buffer whose head stride is rounded up to 8 elements and returned as a [..., :hd] view.  Rows then start
+    16-byte aligned, so the tensor-core kernel can fetch them with TMA instead of its 32-bit staging loads; the
+    padding is never read (the tensor map's inner extent is hd) and costs no extra pass over the data.
+    """
+    hd = x.size(-1)
+    if hd % 8 == 0:
+        return x.to(torch.bfloat16)
+    hd8 = (hd + 7) // 8 * 8
+    buf = torch.empty(*x.shape[:-1], hd8, dtype=torch.bfloat16, device=x.device)
+    view = buf[..., :hd]
+    view.copy_(x)
+    return view
+
+
 def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool, left: int,
                    right: int, q_valid: Optional[torch.Tensor] = None, k_valid: Optional[torch.Tensor] = None,
                    out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -66,6 +84,6 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: 
     to bf16 (the kernels' arithmetic type: bf16 operands, fp32 accumulation) and the result is cast back.
     """
     out_dtype = out_dtype or q.dtype
-    o = ops.gqa_swa_prefill(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), q_valid, k_valid,
+    o = ops.gqa_swa_prefill(_to_kernel_layout(q), _to_kernel_layout(k), _to_kernel_layout(v), q_valid, k_valid,
                             float(scale), bool(causal), int(left), int(right))
     return o.to(out_dtype)
