@@ -31,5 +31,5 @@ skip = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 for (c, role, tag) in recs[skip:skip + lim]:
     base = tag & ~0xf
     nm = names.get(tag) or {0x110: "v ready j=", 0x120: "p0 ready j=", 0x130: "p1 ready j=", 0x200: "wait s j=", 0x210: "s ready j=",
-                            0x220: "p written j=", 0x310: "k slot free j="}.get(base, hex(base)) + str(tag & 0xf)
+                            0x220: "p written j=", 0x250: "  S in regs j=", 0x260: "  max/rescale done j=", 0x270: "  exp done j=", 0x310: "k slot free j="}.get(base, hex(base)) + str(tag & 0xf)
     print(f"{c - t0:9d}  {rolename[role]}  {nm}")

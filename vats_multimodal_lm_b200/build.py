@@ -16,6 +16,7 @@ OUT = os.path.join(CSRC, "libvats_attn.so")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "--use_fast_math", "-Xptxas", "-v", *([f"-DVATS_MBAR_TIMEOUT_CYCLES={os.environ['VATS_MBAR_TIMEOUT_CYCLES']}"] if os.environ.get("VATS_MBAR_TIMEOUT_CYCLES") else []),
+    *(["-DVATS_ENABLE_TRACE"] if os.environ.get("VATS_ENABLE_TRACE") else []),
 ]
 
 

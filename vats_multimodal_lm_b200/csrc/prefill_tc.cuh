@@ -51,6 +51,8 @@ struct TcParams {
   unsigned div_qb[2], div_pairs[2], div_g[2];  // magic (multiplier, shift) pairs for division by q_blocks / pairs / G
   unsigned long long* trace;  // debug: block 0 appends (tag, clock64) pairs here (NULL = off); [0] = count
   int trace_cap;
+  int order_softmax; // 1: the two softmax warpgroups take turns in the exponential phase (staggers the ping-pong)
+  int exp_f16;       // 1: exponentials as packed fp16 (two per MUFU op), widened to fp32 for the row sum and bf16 P
   int exp_poly;      // 1: on unmasked tiles half of the exponentials run on the FMA pipe (degree-3 polynomial)
 };
 
@@ -63,6 +65,7 @@ struct TcSmemBarriers {
   uint64_t s_full[2];
   uint64_t p_full[2];
   uint64_t o_full[2];
+  uint64_t turn[2];      // turn[t]: warpgroup t may run its exponential phase (the other one finished its own)
   uint64_t o_empty[2];   // the softmax warpgroup has read O_t out of TMEM: the next item's P.V may overwrite it
   uint32_t tmem_base;
   uint32_t pad;
@@ -127,6 +130,7 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 
 // Debug timeline: one thread per role of block 0 appends (tag, SM clock) records to its own lane of the buffer
 // (plain stores, no atomics, so the probe costs a few cycles): trace[role][i] = {tag, clock}, trace_cap records/role.
+#if defined(VATS_ENABLE_TRACE)
 struct TcTracer {
   unsigned long long* base;
   int n, cap;
@@ -141,6 +145,12 @@ struct TcTracer {
     }
   }
 };
+#else
+struct TcTracer {  // production build: the probes compile to nothing (build with -DVATS_ENABLE_TRACE to record)
+  __device__ __forceinline__ TcTracer(const TcParams&, int) {}
+  __device__ __forceinline__ void operator()(unsigned) {}
+};
+#endif
 
 // One work item: (sequence n, KV group g, head pair, 128-token query block).
 struct TcWork {
@@ -148,6 +158,7 @@ struct TcWork {
   int t_first, n_tiles;  // KV tile range (n_tiles <= 0: nothing to attend)
   bool active1;          // the pair's second head exists
 };
+
 // n / d for n < 2^31 with a host-computed (multiplier, shift) pair — an integer division costs ~125 cycles on the
 // single-lane roles, and every role decodes every work item.
 __host__ __device__ __forceinline__ void tc_fastdiv(unsigned n, const unsigned (&magic)[2], unsigned d, unsigned* q,
@@ -226,6 +237,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->p_full[t]), 128);
       mbar_init(smem_u32(&bars->o_full[t]), 1);
       mbar_init(smem_u32(&bars->o_empty[t]), 128);
+      mbar_init(smem_u32(&bars->turn[t]), 128);
     }
     const uint32_t kv_arrivals = P.kv_ldg ? kTcLoaderThreads : 1;
     for (int s = 0; s < kTcMaxStages; ++s) {
@@ -288,7 +300,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < wk.n_tiles; ++j) {
               const int k0 = (wk.t_first + j) * kTcBlockN;
               mbar_wait(smem_u32(&empty[slot]), ph ^ 1u);
-              if (is_k) trace(0x310 + j);
+              if (is_k) trace(0x310 + (j & 15));
               const uint32_t bar = smem_u32(&full[slot]);
               mbar_expect_tx(bar, tile_bytes);
               for (int c = 0; c < P.regions; ++c)
@@ -409,10 +421,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t v_lo = v_lo_base + (uint32_t)vs * tile_step;
           const uint32_t k_lo = k_lo_base + (uint32_t)ks * tile_step;
           mbar_wait(smem_u32(&bars->v_full[vs]), vph);
-          if (leader) trace(0x110 + j);
+          if (leader) trace(0x110 + (j & 15));
           // ---- tile 0
           mbar_wait(p_bar0, pc[0] & 1u);
-          if (leader) trace(0x120 + j);
+          if (leader) trace(0x120 + (j & 15));
           ++pc[0];
           if (j == 0) mbar_wait(smem_u32(&bars->o_empty[0]), (qn[0] & 1u) ^ 1u);  // previous item's O_0 was read out
           tc_fence_after();
@@ -427,7 +439,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           // ---- tile 1
           if (active1) {
             mbar_wait(p_bar1, pc[1] & 1u);
-            if (leader) trace(0x130 + j);
+            if (leader) trace(0x130 + (j & 15));
             ++pc[1];
             if (j == 0) mbar_wait(smem_u32(&bars->o_empty[1]), (qn[1] & 1u) ^ 1u);
             tc_fence_after();
@@ -465,6 +477,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     const uint32_t tO = tmem + lane_base + 256 + (uint32_t)t * 128;
     TcTracer trace(P, 2 + t);
     uint32_t sc = 0u;   // S phases consumed by this tile (running across items)
+    uint32_t tk = 0u;   // exponential phases run in turn with the other warpgroup so far
     uint32_t qn = 0u;   // items in which this tile took part so far
 
     for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
@@ -476,6 +489,17 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
 
     float l_run = 0.f;
     float m_used = -INFINITY;  // reference maximum in scaled-log2 units; -inf = not set yet
+    // KV tiles [full_first, full_last] are allowed for every row of the block: no per-element predicate there
+    int full_first, full_last;
+    {
+      int q_last = q0 + kTcBlockM - 1;
+      if (q_last > a.Tq - 1) q_last = a.Tq - 1;
+      long long lo = key_lo(a.mask, q_last);   // tightest lower bound
+      long long hi = key_hi(a.mask, q0);       // tightest upper bound (already <= Tk - 1)
+      if (lo < 0) lo = 0;
+      full_first = lo > (long long)a.Tk ? (a.Tk >> 7) + 1 : ((int)lo + kTcBlockN - 1) >> 7;
+      full_last = hi < 0 ? -1 : (((int)hi + 1) >> 7) - 1;
+    }
 
     if (tile_active && n_tiles > 0) {
       if (P.q_ldg) {
@@ -490,9 +514,9 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       for (int j = 0; j < n_tiles; ++j) {
         const int tile = t_first + j;
         const int k0 = tile * kTcBlockN;
-        if (r == 0) trace(0x200 + j);
+        if (r == 0) trace(0x200 + (j & 15));
         mbar_wait(smem_u32(&bars->s_full[t]), sc & 1u);
-        if (r == 0) trace(0x210 + j);
+        if (r == 0) trace(0x210 + (j & 15));
         ++sc;
         tc_fence_after();
         uint32_t sr[128];
@@ -501,9 +525,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         tmem_ld_32x32b_x32(tS + 64, sr + 64);
         tmem_ld_32x32b_x32(tS + 96, sr + 96);
         tmem_ld_wait();
+        if (r == 0) trace(0x250 + (j & 15));
 
         // ---- predicate (edge tiles only)
-        const bool full = tile_is_full(a.mask, tile, q0, kTcBlockM, kTcBlockN);
+        const bool full = tile >= full_first && tile <= full_last;  // == tile_is_full(a.mask, tile, q0, 128, 128)
         if (!full || a.k_valid != nullptr) {
           uint32_t kbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
           if (a.k_valid != nullptr) {
@@ -526,16 +551,15 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         }
 
         // ---- row max of this tile (raw logits), in-thread
-        float mt0 = __uint_as_float(sr[0]), mt1 = __uint_as_float(sr[1]), mt2 = __uint_as_float(sr[2]),
-              mt3 = __uint_as_float(sr[3]);
+        float mx[8];
 #pragma unroll
-        for (int c = 4; c < 128; c += 4) {
-          mt0 = fmaxf(mt0, __uint_as_float(sr[c]));
-          mt1 = fmaxf(mt1, __uint_as_float(sr[c + 1]));
-          mt2 = fmaxf(mt2, __uint_as_float(sr[c + 2]));
-          mt3 = fmaxf(mt3, __uint_as_float(sr[c + 3]));
-        }
-        const float mt = fmaxf(fmaxf(mt0, mt1), fmaxf(mt2, mt3)) * a.scale_log2;  // scaled-log2 units (scale > 0)
+        for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(sr[i]);
+#pragma unroll
+        for (int c = 8; c < 128; c += 8)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __uint_as_float(sr[c + i]));
+        const float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) *
+                         a.scale_log2;  // scaled-log2 units (scale > 0)
 
         // ---- lazy rescale of the running state
         float factor = 1.f;
@@ -557,6 +581,12 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           }
         }
 
+        // ---- the exponential phase is the MUFU-bound part: when both tiles are live the two warpgroups take turns
+        //      in it, which staggers them by half a period — one tile's softmax then overlaps the other tile's MMAs
+        //      instead of both softmaxes (and then both MMA batches) running in lock-step.
+        if (r == 0) trace(0x260 + (j & 15));
+        const bool ordered = P.order_softmax && wk.active1;
+        if (ordered) mbar_wait(smem_u32(&bars->turn[t]), t == 0 ? ((tk & 1u) ^ 1u) : (tk & 1u));
         // ---- p = exp2(s*scale_log2 - m_used), row sum, pack to bf16, write P over S.
         //      The scale/subtract and the row sums run as packed f32x2 operations (FFMA2 / FADD2).  The MUFU pipe
         //      (16 ex2/clk/SM) needs as long for a 128x128 tile as the tensor core needs for its two MMAs, so on
@@ -569,7 +599,22 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         const float2 nm2 = make_float2(-mref, -mref);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
         uint32_t pk[64];
-        if (P.exp_poly && full && a.k_valid == nullptr) {
+        if (P.exp_f16) {
+          // packed-fp16 exponentials: x -> f16x2 (11-bit mantissa: the argument keeps ~3 more bits than bf16 P needs),
+          // one MUFU op per pair, widened back to fp32 for the row sum and the bf16 pack.  (kind::f16 MMAs cannot mix
+          // an fp16 A with a bf16 B, so P stays bf16.)
+#pragma unroll
+          for (int c = 0; c < 128; c += 4) {
+            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, nm2);
+            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), sc2, nm2);
+            const float2 p0 = f16x2_to_float2(ex2_f16x2(pack_f16x2(x0.x, x0.y)));
+            const float2 p1 = f16x2_to_float2(ex2_f16x2(pack_f16x2(x1.x, x1.y)));
+            sum_a = __fadd2_rn(sum_a, p0);
+            sum_b = __fadd2_rn(sum_b, p1);
+            pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
+            pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+          }
+        } else if (P.exp_poly && full && a.k_valid == nullptr) {
           const float2 magic = make_float2(12582912.f, 12582912.f);
           const float2 nmagic = make_float2(-12582912.f, -12582912.f);
           const float2 neg1 = make_float2(-1.f, -1.f);
@@ -609,12 +654,17 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         l_run += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        if (ordered) {
+          mbar_arrive(smem_u32(&bars->turn[t ^ 1]));
+          ++tk;
+        }
+        if (r == 0) trace(0x270 + (j & 15));
         tmem_st_32x32b_x32(tS + 0, pk + 0);
         tmem_st_32x32b_x32(tS + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[t]));
-        if (r == 0) trace(0x220 + j);
+        if (r == 0) trace(0x220 + (j & 15));
       }
     }
 

@@ -241,10 +241,11 @@ __device__ __forceinline__ uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
 
-// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor for kind::f16 with bf16 inputs (A optionally fp16) and fp32 accumulation.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major,
+                                                       int a_is_f16 = 0) {
   return (1u << 4)                      // c_format = F32
-         | (1u << 7)                    // a_format = BF16
+         | ((a_is_f16 ? 0u : 1u) << 7)  // a_format = BF16 (1) or F16 (0)
          | (1u << 10)                   // b_format = BF16
          | ((uint32_t)a_mn_major << 15) // a_major
          | ((uint32_t)b_mn_major << 16) // b_major
@@ -302,6 +303,28 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// pack two fp32 into f16x2 (lo = a, hi = b)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// two exponentials per MUFU instruction: packed fp16 in, packed fp16 out
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t h) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h));
+  return make_float2(lo, hi);
 }
 // pack two fp32 into bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

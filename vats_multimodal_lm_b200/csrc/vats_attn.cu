@@ -243,6 +243,18 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
       exp_poly = (e && atoi(e) == 1) ? 1 : 0;
     }
     P.exp_poly = exp_poly;
+    static int order = -1;
+    if (order < 0) {
+      const char* e = getenv("VATS_PREFILL_ORDER_SOFTMAX");  // tuning knob
+      order = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    P.order_softmax = order;
+    static int exp_f16 = -1;
+    if (exp_f16 < 0) {
+      const char* e = getenv("VATS_PREFILL_EXP_F16");  // tuning knob
+      exp_f16 = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    P.exp_f16 = exp_f16;
   }
   // ring depths: fill the 227 KB of shared memory (also pins one CTA per SM, which owns all 512 TMEM columns)
   const int tile_bytes = P.regions * vats::kTcRegionBytes;
