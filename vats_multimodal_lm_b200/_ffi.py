@@ -12,7 +12,8 @@ import threading
 from typing import Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvats_attn.so")
+# VATS_ATTN_LIB lets the tools/ scripts load a differently-built copy (e.g. the -DVATS_ENABLE_TRACE build)
+LIB_PATH = os.environ.get("VATS_ATTN_LIB") or os.path.join(_HERE, "csrc", "libvats_attn.so")
 
 KERNEL_AUTO = 0
 KERNEL_TCGEN05 = 1

@@ -45,15 +45,15 @@ struct TcParams {
   int q_blocks;      // ceil(Tq / 128)
   int pairs;         // ceil(hpg / 2) head pairs per KV group
   int nk, nv;        // ring depths
-  int q_ldg, kv_ldg; // 1: the tensor is not TMA-addressable (row starts only 4-byte aligned): LDG staging instead
   int o_vec16;       // 1: O rows may be written with 16-byte stores
+  int o_stage;       // O write-out: 0 = per-thread row stores; 1 = per-warp shared-memory staging + TMA tile stores
+                     // (tmap_o is valid); 2 = the same staging, written out with coalesced 32-bit stores (rows only
+                     // 4-byte aligned, e.g. head_dim 66)
   int num_work;      // N * G * pairs * q_blocks work items, walked round-robin by the persistent CTAs
   unsigned div_qb[2], div_pairs[2], div_g[2];  // magic (multiplier, shift) pairs for division by q_blocks / pairs / G
   unsigned long long* trace;  // debug: block 0 appends (tag, clock64) pairs here (NULL = off); [0] = count
   int trace_cap;
   int order_softmax; // 1: the two softmax warpgroups take turns in the exponential phase (staggers the ping-pong)
-  int exp_f16;       // 1: exponentials as packed fp16 (two per MUFU op), widened to fp32 for the row sum and bf16 P
-  int exp_poly;      // 1: on unmasked tiles half of the exponentials run on the FMA pipe (degree-3 polynomial)
 };
 
 struct TcSmemBarriers {
@@ -71,8 +71,11 @@ struct TcSmemBarriers {
   uint32_t pad;
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int regions, int nk, int nv) {
-  return (size_t)(2 + nk + nv) * regions * kTcRegionBytes + 1024 /*alignment slack*/ + sizeof(TcSmemBarriers);
+constexpr int kTcOStageBytes = 32 * 128;  // per softmax warp: 32 rows x 64 bf16, one 128B-swizzled TMA store box
+
+__host__ __device__ inline size_t tc_smem_bytes(int regions, int nk, int nv, int o_stage) {
+  return (size_t)(2 + nk + nv) * regions * kTcRegionBytes + (o_stage ? 8 * kTcOStageBytes : 0) +
+         1024 /*alignment slack*/ + sizeof(TcSmemBarriers);
 }
 
 // Stage rows [row0, row0+128) x hd of a row-strided bf16 matrix into a 128B-swizzled K-major tile (the layout a
@@ -204,9 +207,14 @@ __device__ __forceinline__ TcWork tc_decode_work(const TcParams& P, int w) {
   return k;
 }
 
+// kLdg = false: Q / K / V arrive by TMA.  kLdg = true: at least one of them is not TMA-addressable (row starts only
+// 4-byte aligned) and all three are staged with LDG loaders instead.  Two instantiations rather than a run-time
+// switch: the per-item code of a short-sequence launch otherwise thrashes the instruction cache.
+template <bool kLdg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
-                  const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v) {
+                  const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                  const __grid_constant__ CUtensorMap tmap_o) {
   using namespace ptx;
   extern __shared__ unsigned char smem_raw[];
   const PrefillParams& a = P.a;
@@ -218,17 +226,21 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t sQ = base;
   const uint32_t sK = sQ + 2 * tile_bytes;
   const uint32_t sV = sK + (uint32_t)P.nk * tile_bytes;
-  TcSmemBarriers* bars =
-      reinterpret_cast<TcSmemBarriers*>(smem_raw + (base - raw) + (size_t)(2 + P.nk + P.nv) * tile_bytes);
+  const uint32_t sO = sV + (uint32_t)P.nv * tile_bytes;   // 8 x kTcOStageBytes when P.o_stage
+  TcSmemBarriers* bars = reinterpret_cast<TcSmemBarriers*>(smem_raw + (base - raw) + (size_t)(2 + P.nk + P.nv) * tile_bytes +
+                                                           (P.o_stage ? 8 * kTcOStageBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
   if (warp == 8 && lane == 0) {
-    prefetch_tmap(&tmap_q);
-    prefetch_tmap(&tmap_k);
-    prefetch_tmap(&tmap_v);
+    if (!kLdg) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    if (P.o_stage == 1) prefetch_tmap(&tmap_o);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->q_full[t]), 1);
       mbar_init(smem_u32(&bars->q_fixed[t]), 128);
@@ -239,7 +251,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(smem_u32(&bars->o_empty[t]), 128);
       mbar_init(smem_u32(&bars->turn[t]), 128);
     }
-    const uint32_t kv_arrivals = P.kv_ldg ? kTcLoaderThreads : 1;
+    const uint32_t kv_arrivals = kLdg ? kTcLoaderThreads : 1;
     for (int s = 0; s < kTcMaxStages; ++s) {
       mbar_init(smem_u32(&bars->k_full[s]), kv_arrivals);
       mbar_init(smem_u32(&bars->k_empty[s]), 1);
@@ -261,14 +273,14 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     // =========================================================== warpgroup 2: producers (warps 8-10) + MMA issuer (11)
     setmaxnreg_dec<80>();
   if (warp <= 10) {
-    if (!P.kv_ldg) {
+    if (!kLdg) {
       // ---- TMA: three issuing lanes — warp 8 feeds the K ring, warp 9 the V ring, warp 10 the Q tiles.  One thread
       //      needs ~300 cycles per box (tools/micro/tma_bw.cu), so a single producer would serialise the 8 boxes an
       //      item starts with; the rings run continuously across items.
       if (lane == 0) {
         TcTracer trace(P, 0);
         if (warp == 10) {
-          if (!P.q_ldg) {
+          {
             uint32_t qn[2] = {0u, 0u};      // items in which tile t took part so far
             for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
               const TcWork wk = tc_decode_work(P, w);
@@ -398,8 +410,8 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         const bool active1 = wk.active1;
         const int n_tiles = wk.n_tiles;
         // ---- Q tiles of this item, first K tile, S(0) for both heads
-        mbar_wait(smem_u32(P.q_ldg ? &bars->q_fixed[0] : &bars->q_full[0]), qn[0] & 1u);
-        if (active1) mbar_wait(smem_u32(P.q_ldg ? &bars->q_fixed[1] : &bars->q_full[1]), qn[1] & 1u);
+        mbar_wait(smem_u32(kLdg ? &bars->q_fixed[0] : &bars->q_full[0]), qn[0] & 1u);
+        if (active1) mbar_wait(smem_u32(kLdg ? &bars->q_fixed[1] : &bars->q_full[1]), qn[1] & 1u);
         if (leader) trace(0x100);
         mbar_wait(smem_u32(&bars->k_full[ks]), kph);
         if (leader) trace(0x101);
@@ -502,7 +514,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     }
 
     if (tile_active && n_tiles > 0) {
-      if (P.q_ldg) {
+      if (kLdg) {
         // the 128 threads of this warpgroup stage their own Q tile, once the previous item's MMAs are done with it
         mbar_wait(smem_u32(&bars->q_empty[t]), (qn & 1u) ^ 1u);
         const __nv_bfloat16* qbase = a.q + n * a.qs_n + (long long)head * a.qs_h;
@@ -543,11 +555,17 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           long long hi = key_hi(a.mask, tok) - k0;
           const int lo_c = lo < 0 ? 0 : (lo > 128 ? 128 : (int)lo);
           const int hi_c = hi < -1 ? -1 : (hi > 127 ? 127 : (int)hi);
+          // allowed columns = [lo_c, hi_c] & k_valid bits, as four 32-bit words: two instructions per element below
 #pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            const bool ok = (c >= lo_c) && (c <= hi_c) && ((kbits[c >> 5] >> (c & 31)) & 1u);
-            if (!ok) sr[c] = 0xff800000u;  // -inf
+          for (int w = 0; w < 4; ++w) {
+            const int l = lo_c - 32 * w, h = hi_c - 32 * w;
+            const uint32_t ml = l <= 0 ? 0xffffffffu : (l >= 32 ? 0u : 0xffffffffu << l);
+            const uint32_t mh = h >= 31 ? 0xffffffffu : (h < 0 ? 0u : 0xffffffffu >> (31 - h));
+            kbits[w] &= ml & mh;
           }
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (!((kbits[c >> 5] >> (c & 31)) & 1u)) sr[c] = 0xff800000u;  // -inf
         }
 
         // ---- row max of this tile (raw logits), in-thread
@@ -588,59 +606,16 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         const bool ordered = P.order_softmax && wk.active1;
         if (ordered) mbar_wait(smem_u32(&bars->turn[t]), t == 0 ? ((tk & 1u) ^ 1u) : (tk & 1u));
         // ---- p = exp2(s*scale_log2 - m_used), row sum, pack to bf16, write P over S.
-        //      The scale/subtract and the row sums run as packed f32x2 operations (FFMA2 / FADD2).  The MUFU pipe
-        //      (16 ex2/clk/SM) needs as long for a 128x128 tile as the tensor core needs for its two MMAs, so on
-        //      unmasked tiles every other pair of elements takes exp2 on the FMA pipe instead: round to nearest
-        //      integer with the 1.5*2^23 trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative
-        //      error 7.5e-5, 50x below bf16 rounding), integer part added into the exponent field.  Masked tiles
-        //      keep the MUFU path, where ex2(-inf) is exactly 0.
+        //      The scale/subtract and the row sums run as packed f32x2 operations (FFMA2 / FADD2), the exponentials on
+        //      the MUFU pipe (ex2(-inf) is exactly 0 for masked keys).  Two alternatives were built and measured on
+        //      B200 — half of the exponentials as a degree-3 polynomial on the FMA pipe, and packed-fp16 ex2 — and
+        //      both were slower: this phase is issue/latency-bound, not MUFU-bound.
         const float mref = (m_used == -INFINITY) ? 0.f : m_used;
         const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
         const float2 nm2 = make_float2(-mref, -mref);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
         uint32_t pk[64];
-        if (P.exp_f16) {
-          // packed-fp16 exponentials: x -> f16x2 (11-bit mantissa: the argument keeps ~3 more bits than bf16 P needs),
-          // one MUFU op per pair, widened back to fp32 for the row sum and the bf16 pack.  (kind::f16 MMAs cannot mix
-          // an fp16 A with a bf16 B, so P stays bf16.)
-#pragma unroll
-          for (int c = 0; c < 128; c += 4) {
-            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, nm2);
-            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), sc2, nm2);
-            const float2 p0 = f16x2_to_float2(ex2_f16x2(pack_f16x2(x0.x, x0.y)));
-            const float2 p1 = f16x2_to_float2(ex2_f16x2(pack_f16x2(x1.x, x1.y)));
-            sum_a = __fadd2_rn(sum_a, p0);
-            sum_b = __fadd2_rn(sum_b, p1);
-            pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
-            pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-          }
-        } else if (P.exp_poly && full && a.k_valid == nullptr) {
-          const float2 magic = make_float2(12582912.f, 12582912.f);
-          const float2 nmagic = make_float2(-12582912.f, -12582912.f);
-          const float2 neg1 = make_float2(-1.f, -1.f);
-          const float2 c0 = make_float2(0.9999280571937561f, 0.9999280571937561f);
-          const float2 c1 = make_float2(0.6932609677314758f, 0.6932609677314758f);
-          const float2 c2 = make_float2(0.2426111400127411f, 0.2426111400127411f);
-          const float2 c3 = make_float2(0.05517186224460602f, 0.05517186224460602f);
-#pragma unroll
-          for (int c = 0; c < 128; c += 4) {
-            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, nm2);
-            float2 x1 = __ffma2_rn(make_float2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), sc2, nm2);
-            const float2 p0 = make_float2(ex2(x0.x), ex2(x0.y));
-            x1 = make_float2(fmaxf(x1.x, -126.f), fmaxf(x1.y, -126.f));
-            const float2 r = __fadd2_rn(x1, magic);                       // integer part lands in the low mantissa bits
-            const float2 fr = __ffma2_rn(__fadd2_rn(r, nmagic), neg1, x1); // x - round(x)  in [-0.5, 0.5]
-            float2 q = __ffma2_rn(fr, c3, c2);
-            q = __ffma2_rn(fr, q, c1);
-            q = __ffma2_rn(fr, q, c0);
-            const float2 p1 = make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23)),
-                                          __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
-            sum_a = __fadd2_rn(sum_a, p0);
-            sum_b = __fadd2_rn(sum_b, p1);
-            pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
-            pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-          }
-        } else {
+        {
 #pragma unroll
           for (int c = 0; c < 128; c += 4) {
             const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), sc2, nm2);
@@ -668,30 +643,105 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       }
     }
 
-    // ---- epilogue: O / l -> bf16 -> global.  The whole O row is pulled out of TMEM first and the accumulator is
-    //      handed back (o_empty) before the global stores, so the next item's MMAs overlap this item's write-out.
+    // ---- epilogue: O / l -> bf16 -> global.  The accumulator is handed back (o_empty) as soon as its last chunk is
+    //      out of TMEM, so the next item's MMAs overlap this item's write-out.
     //      (tcgen05.ld is warp-collective: every lane runs the loads; only the stores are predicated on the row.)
     if (tile_active) {
       const bool do_store = tok < a.Tq;
       bool qok = true;
       if (do_store && a.q_valid != nullptr) qok = a.q_valid[(long long)n * a.Tq + tok] != 0;
       const float inv = (qok && l_run > 0.f && n_tiles > 0) ? 1.f / l_run : 0.f;
-      __nv_bfloat16* orow = a.o + n * a.os_n + (long long)tok * a.os_t + (long long)head * a.os_h;
       if (n_tiles > 0) {
         if (r == 0) trace(0x230);
         mbar_wait(smem_u32(&bars->o_full[t]), qn & 1u);
         if (r == 0) trace(0x231);
         tc_fence_after();
       }
+      if (P.o_stage) {
+        // Each warp transposes its 32 rows through a private 4 KB staging tile (64 columns at a time, written in the
+        // 128B-swizzle pattern): rows are 2-4 KB apart in global memory, so per-thread row stores would cost the LSU
+        // one transaction per 16 bytes.  The tile then leaves with one TMA tile store issued by lane 0 (TMA clips
+        // rows >= Tq and columns >= hd) or, when O rows are only 4-byte aligned, with coalesced 32-bit stores.
+        const uint32_t stage = sO + (uint32_t)warp * kTcOStageBytes;
+        const int row_w = q0 + (warp & 3) * 32;  // first token of this warp's 32 rows
+#pragma unroll 1
+        for (int cb = 0; cb < P.hd_pad; cb += 64) {
+          // the previous store of this warp must have finished reading the staging tile
+          if (P.o_stage == 1 && lane == 0) bulk_wait_group_read0();
+          __syncwarp();
+#pragma unroll 1
+          for (int c = cb; c < cb + 64 && c < P.hd_pad; c += 32) {   // 32 accumulator columns at a time
+            uint32_t tmp[32];
+            if (n_tiles > 0) {
+              tmem_ld_32x32b_x16(tO + c, tmp);
+              if (c + 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + c + 16, tmp + 16);
+              tmem_ld_wait();
+              if (c + 32 >= P.hd_pad) {   // last chunk is out of TMEM: hand the accumulator back
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->o_empty[t]));
+                ++qn;
+              }
+            } else {
 #pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {        // 32 accumulator columns at a time (keeps the row out of local memory)
-        if (qd * 32 < P.hd_pad) {
+              for (int i = 0; i < 32; ++i) tmp[i] = 0u;
+            }
+            const uint32_t u0 = (uint32_t)(c - cb) >> 3;   // first 16-byte unit of this chunk within the 128-byte row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t x = pack_bf16x2(__uint_as_float(tmp[8 * i + 0]) * inv, __uint_as_float(tmp[8 * i + 1]) * inv);
+              const uint32_t y = pack_bf16x2(__uint_as_float(tmp[8 * i + 2]) * inv, __uint_as_float(tmp[8 * i + 3]) * inv);
+              const uint32_t z = pack_bf16x2(__uint_as_float(tmp[8 * i + 4]) * inv, __uint_as_float(tmp[8 * i + 5]) * inv);
+              const uint32_t w = pack_bf16x2(__uint_as_float(tmp[8 * i + 6]) * inv, __uint_as_float(tmp[8 * i + 7]) * inv);
+              const uint32_t dst = stage + (uint32_t)lane * 128u + (((u0 + i) ^ ((uint32_t)lane & 7u)) << 4);
+              // (columns >= hd_pad of the last chunk hold stale accumulator words; TMA clips everything >= hd)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+            }
+          }
+          if (P.o_stage == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row_w < a.Tq) {
+              tma_store_4d(&tmap_o, stage, cb, head, row_w, n);
+              bulk_commit_group();
+            }
+          } else {
+            __syncwarp();
+            // word index f = row * wv + w walks lane, lane + 32, ...: consecutive lanes write consecutive words of a row
+            const int wv = (a.hd - cb >= 64 ? 64 : a.hd - cb) >> 1;   // valid 32-bit words per row in this chunk
+            if (wv > 0) {
+              uint32_t* obase = reinterpret_cast<uint32_t*>(a.o + n * a.os_n + (long long)head * a.os_h + cb);
+              const int dq = 32 / wv, dr = 32 % wv;
+              int row = lane / wv, w = lane - row * wv;
+              const int rows_ok = a.Tq - row_w;   // rows of this warp below the end of the sequence
+              while (row < 32) {
+                if (row < rows_ok) {
+                  const uint32_t src = stage + (uint32_t)row * 128u + ((((uint32_t)w >> 2) ^ ((uint32_t)row & 7u)) << 4) +
+                                       (((uint32_t)w & 3u) << 2);
+                  uint32_t val;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val) : "r"(src) : "memory");
+                  obase[(((long long)(row_w + row) * a.os_t) >> 1) + w] = val;
+                }
+                w += dr;
+                row += dq;
+                if (w >= wv) {
+                  w -= wv;
+                  ++row;
+                }
+              }
+            }
+            __syncwarp();   // the tile is rewritten by the next chunk
+          }
+        }
+      } else {
+        __nv_bfloat16* orow = a.o + n * a.os_n + (long long)tok * a.os_t + (long long)head * a.os_h;
+#pragma unroll 1
+        for (int cb = 0; cb < P.hd_pad; cb += 32) {  // 32 accumulator columns at a time (keeps the row out of local memory)
           uint32_t tmp[32];
           if (n_tiles > 0) {
-            tmem_ld_32x32b_x16(tO + qd * 32, tmp);
-            if (qd * 32 + 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + qd * 32 + 16, tmp + 16);
+            tmem_ld_32x32b_x16(tO + cb, tmp);
+            if (cb + 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + cb + 16, tmp + 16);
             tmem_ld_wait();
-            if (qd * 32 + 32 >= P.hd_pad) {   // last chunk is out of TMEM: hand the accumulator back before storing
+            if (cb + 32 >= P.hd_pad) {   // last chunk is out of TMEM: hand the accumulator back before storing
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->o_empty[t]));
               ++qn;
@@ -705,30 +755,21 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               w[i] = pack_bf16x2(__uint_as_float(tmp[2 * i]) * inv, __uint_as_float(tmp[2 * i + 1]) * inv);
+            if (P.o_vec16) {
 #pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {
-              const int c = qd * 32 + hc * 16;
-              if (c < P.hd_pad) {
-                if (P.o_vec16 && c + 16 <= a.hd) {
-                  *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[hc * 8 + 0], w[hc * 8 + 1], w[hc * 8 + 2], w[hc * 8 + 3]);
-                  *reinterpret_cast<uint4*>(orow + c + 8) =
-                      make_uint4(w[hc * 8 + 4], w[hc * 8 + 5], w[hc * 8 + 6], w[hc * 8 + 7]);
+              for (int u = 0; u < 4; ++u)
+                if (cb + u * 8 < a.hd)   // hd % 8 == 0 here: 16-byte units are all-in or all-out
+                  *reinterpret_cast<uint4*>(orow + cb + u * 8) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+            } else {
+              const bool al4 = (reinterpret_cast<uintptr_t>(orow) & 3u) == 0;   // even hd/strides: pairs are 4-byte aligned
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int e = cb + 2 * i;
+                if (e + 1 < a.hd && al4) {
+                  *reinterpret_cast<uint32_t*>(orow + e) = w[i];
                 } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int e = c + 2 * i;
-                    const uint32_t wv = w[hc * 8 + i];
-                    if (e + 1 < a.hd) {
-                      if ((reinterpret_cast<uintptr_t>(orow + e) & 3u) == 0) {
-                        *reinterpret_cast<uint32_t*>(orow + e) = wv;
-                      } else {
-                        reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(wv & 0xffffu);
-                        reinterpret_cast<uint16_t*>(orow)[e + 1] = (uint16_t)(wv >> 16);
-                      }
-                    } else if (e < a.hd) {
-                      reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(wv & 0xffffu);
-                    }
-                  }
+                  if (e < a.hd) reinterpret_cast<uint16_t*>(orow)[e] = (uint16_t)(w[i] & 0xffffu);
+                  if (e + 1 < a.hd) reinterpret_cast<uint16_t*>(orow)[e + 1] = (uint16_t)(w[i] >> 16);
                 }
               }
             }
@@ -742,6 +783,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
   }
 
   // ---- teardown
+  if (P.o_stage == 1 && warp < 8 && lane == 0) bulk_wait_group0();  // staged O tiles must be out before the CTA's smem goes away
   tc_fence_before();
   __syncthreads();
   if (warp == 11) {

@@ -230,61 +230,57 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.pairs = (P.a.hpg + 1) / 2;
   // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
-  P.q_ldg = any_ldg ? 1 : 0;
-  P.kv_ldg = any_ldg ? 1 : 0;
   P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1
                   : 0;
   {
-    static int exp_poly = -1;
-    if (exp_poly < 0) {
-      const char* e = getenv("VATS_PREFILL_EXP_POLY");  // tuning knob
-      exp_poly = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    P.exp_poly = exp_poly;
     static int order = -1;
     if (order < 0) {
       const char* e = getenv("VATS_PREFILL_ORDER_SOFTMAX");  // tuning knob
       order = (e && atoi(e) == 0) ? 0 : 1;
     }
     P.order_softmax = order;
-    static int exp_f16 = -1;
-    if (exp_f16 < 0) {
-      const char* e = getenv("VATS_PREFILL_EXP_F16");  // tuning knob
-      exp_f16 = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    P.exp_f16 = exp_f16;
   }
   // ring depths: fill the 227 KB of shared memory (also pins one CTA per SM, which owns all 512 TMEM columns)
   const int tile_bytes = P.regions * vats::kTcRegionBytes;
-  int stages = (int)((227 * 1024 - 1024 - (int)sizeof(vats::TcSmemBarriers) - 2 * tile_bytes) / tile_bytes);
+  const int budget = 227 * 1024 - 1024 - (int)sizeof(vats::TcSmemBarriers) - 2 * tile_bytes;
+  // O leaves through per-warp staging tiles (32 KB of shared memory) whenever the K/V rings keep two slots each:
+  // as TMA tile stores when O is TMA-addressable, else as coalesced 32-bit stores when its rows are 4-byte aligned.
+  {
+    const LoadMode om = plan_load(A.o, A.hd, A.os);
+    static int o_env = -1;
+    if (o_env < 0) {
+      const char* e = getenv("VATS_PREFILL_O_STAGE");  // tuning knob: 0 = per-thread row stores only
+      o_env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool room = (budget - 8 * vats::kTcOStageBytes) / tile_bytes >= 4;
+    P.o_stage = (!o_env || !room || om == LoadMode::kNone) ? 0 : (om == LoadMode::kTma ? 1 : 2);
+  }
+  int stages = (budget - (P.o_stage ? 8 * vats::kTcOStageBytes : 0)) / tile_bytes;
   int nk = stages / 2, nv = stages - nk;
   if (nk > vats::kTcMaxStages) nk = vats::kTcMaxStages;
   if (nv > vats::kTcMaxStages) nv = vats::kTcMaxStages;
   if (nk < 1 || nv < 1) return fail(VATS_ERR_UNSUPPORTED, "tile does not fit shared memory");
   P.nk = nk;
   P.nv = nv;
-  const size_t smem = vats::tc_smem_bytes(P.regions, nk, nv);
+  const size_t smem = vats::tc_smem_bytes(P.regions, nk, nv, P.o_stage);
 
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   std::memset(&mq, 0, sizeof(mq));
   std::memset(&mk, 0, sizeof(mk));
   std::memset(&mv, 0, sizeof(mv));
+  std::memset(&mo, 0, sizeof(mo));
   int rc;
-  if (!P.q_ldg && (rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs)) != VATS_OK) return rc;
-  if (!P.kv_ldg) {
+  if (!any_ldg) {
+    if ((rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs)) != VATS_OK) return rc;
     if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks)) != VATS_OK) return rc;
     if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs)) != VATS_OK) return rc;
   }
+  if (P.o_stage == 1 && (rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32)) != VATS_OK) return rc;
 
   const long long ctas = (long long)A.N * A.G * P.pairs * P.q_blocks;
   if (ctas > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "grid too large");
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
   P.num_work = (int)ctas;
   vats::tc_find_divisor((unsigned)P.q_blocks, P.div_qb);
   vats::tc_find_divisor((unsigned)P.pairs, P.div_pairs);
@@ -293,7 +289,18 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.trace_cap = g_trace_cap;
   int grid = sm_count();
   if (grid > P.num_work) grid = P.num_work;
-  vats::prefill_tc_kernel<<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv);
+  static thread_local size_t smem_set[2] = {0, 0};
+  if (smem > smem_set[any_ldg ? 1 : 0]) {
+    if (any_ldg)
+      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[any_ldg ? 1 : 0] = smem;
+  }
+  if (any_ldg)
+    vats::prefill_tc_kernel<true><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
+  else
+    vats::prefill_tc_kernel<false><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
   return VATS_OK;
