@@ -156,6 +156,40 @@ def test_vit3d_temporal_and_tiny_head_dim_simt():
         check_close(o, ref, f"simt {(N, T, H, G, hd)}")
 
 
+# (N, Tq, Tk, H, G, hd): the one-CTA-per-sequence kernel (Tk <= 32): bulk (dense, odd hd/2) and cp.async staging, every
+# keys-per-pass / heads-per-thread instantiation, Tq != Tk, more sequences than persistent CTAs
+SHORT_SHAPES = [
+    (700, 8, 8, 32, 8, 66), (5, 8, 8, 8, 2, 64), (4, 16, 16, 6, 3, 34), (3, 32, 32, 4, 4, 20), (9, 5, 8, 12, 4, 26),
+    (6, 8, 3, 16, 2, 66), (2, 30, 17, 3, 3, 10), (11, 1, 1, 8, 8, 66), (3, 12, 12, 10, 5, 18), (2, 7, 7, 6, 6, 128),
+]
+
+
+@pytest.mark.parametrize("causal,left,right", [(False, -1, -1), (True, -1, 0), (True, 3, 0), (False, 2, 1)])
+@pytest.mark.parametrize("shape", SHORT_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_short_sequence_kernel_matches_oracle(shape, causal, left, right):
+    N, Tq, Tk, H, G, hd = shape
+    q, k, v = make_qkv(N, Tq, Tk, H, G, hd, seed=71)
+    g = torch.Generator().manual_seed(72)
+    kv = torch.rand(N, Tk, generator=g) > 0.25
+    qv = torch.rand(N, Tq, generator=g) > 0.2
+    scale = 1 / math.sqrt(hd)
+    for (q_valid, k_valid) in [(None, None), (qv, kv)]:
+        ref = oracle_prefill(q, k, v, scale, causal, left, right, q_valid, k_valid)
+        o = run_prefill(q, k, v, scale, causal, left, right, q_valid, k_valid, kernel=SIMT)
+        check_close(o, ref, f"short dense {shape}")
+        # the same values seen through a padded, non-dense layout (head stride rounded up to 8, as the modules do)
+        hp = (hd + 7) // 8 * 8 + 8
+        qp, kp, vp = (torch.zeros(*t.shape[:-1], hp, dtype=t.dtype) for t in (q, k, v))
+        qp[..., :hd], kp[..., :hd], vp[..., :hd] = q, k, v
+        dq, dk, dv = (t.cuda()[..., :hd] for t in (qp, kp, vp))
+        o2 = ops.gqa_swa_prefill(dq, dk, dv, None if q_valid is None else q_valid.cuda(),
+                                 None if k_valid is None else k_valid.cuda(), scale, causal, left, right, SIMT)
+        torch.cuda.synchronize()
+        check_close(o2, ref, f"short strided {shape}")
+        assert torch.equal(o.cpu(), o2.cpu()), "the two staging paths must give identical bits"
+
+
+
 def test_empty_inputs():
     dev = "cuda"
     z = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)

@@ -40,8 +40,18 @@ def main():
     else:
         N, T, H, G, hd, causal, left = W[name]
         q, k, v = rnd((N, T, H, hd), 1, True), rnd((N, T, G, hd), 2, True), rnd((N, T, G, hd), 3, False)
+        f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0)
         for _ in range(reps):
-            o = ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0)
+            o = f()
+        if "--time" in sys.argv:   # CUDA-event timing of 20 further calls (inputs > L2 or L2 flushed by the next call's data)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                o = f()
+            e1.record()
+            torch.cuda.synchronize()
+            print(name, "ms/call", e0.elapsed_time(e1) / 20)
     torch.cuda.synchronize()
     print(name, "ok", float(o.float().abs().mean()))
 

@@ -20,6 +20,7 @@
 #include "mask.cuh"
 #include "prefill_simt.cuh"
 #include "prefill_tc.cuh"
+#include "prefill_short.cuh"
 
 namespace {
 
@@ -220,6 +221,112 @@ int launch_simt(const PrefillArgs& A, cudaStream_t st) {
   return VATS_OK;
 }
 
+// Short sequences (Tk <= 32) with 4-byte aligned rows: one CTA per sequence, see prefill_short.cuh.
+// Returns -1 when the geometry does not qualify (the caller then uses the generic warp kernel).
+int launch_short(const PrefillArgs& A, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VATS_PREFILL_SHORT");  // tuning knob: 0 = always the generic warp kernel
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled || A.Tk > 32 || A.Tk < 1 || A.Tq < 1 || A.N < 1) return -1;
+  if (plan_load(A.q, A.hd, A.qs) == LoadMode::kNone || plan_load(A.k, A.hd, A.ks) == LoadMode::kNone ||
+      plan_load(A.v, A.hd, A.vs) == LoadMode::kNone || plan_load(A.o, A.hd, A.os) == LoadMode::kNone)
+    return -1;
+  vats::ShortParams P;
+  std::memset(&P, 0, sizeof(P));
+  fill_common(P.a, A);
+  const int hpg = P.a.hpg;
+  const int kmax = A.Tk <= 8 ? 8 : (A.Tk <= 16 ? 16 : 32);
+  P.hd2 = A.hd / 2;
+  const long long q_rows = (long long)A.Tq * A.H, kv_rows = (long long)A.Tk * A.G;
+  // bulk (TMA 1-D) staging: every per-sequence block dense and 16-byte aligned
+  auto dense16 = [&](const void* ptr, const int64_t* st3, int heads, long long rows) {
+    return st3[2] == A.hd && st3[1] == (int64_t)heads * A.hd && (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 &&
+           (rows * A.hd * 2) % 16 == 0 && (A.N == 1 || (st3[0] * 2) % 16 == 0);
+  };
+  bool bulk = dense16(A.q, A.qs, A.H, q_rows) && dense16(A.k, A.ks, A.G, kv_rows) && dense16(A.v, A.vs, A.G, kv_rows);
+  {
+    static int bulk_env = -1;
+    if (bulk_env < 0) {
+      const char* e = getenv("VATS_PREFILL_SHORT_BULK");  // tuning knob: 0 = cp.async staging even for dense inputs
+      bulk_env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!bulk_env) bulk = false;
+  }
+  P.o_bulk = bulk && dense16(A.o, A.os, A.H, q_rows) ? 1 : 0;
+  P.pitch = bulk ? P.hd2 : (P.hd2 | 1);
+  if (q_rows * P.pitch > (1 << 22)) return -1;
+  P.q_rows = (int)q_rows;
+  P.kv_rows = (int)kv_rows;
+  P.q_words = ((int)q_rows * P.pitch + 3) & ~3;
+  P.kv_words = ((int)kv_rows * P.pitch + 3) & ~3;
+  P.nss = (P.hd2 + 15) / 16;
+  P.vt_words = P.nss * 32 * (kmax / 2);
+  P.m_rows = A.Tq * hpg;
+  P.m_blocks = (P.m_rows + 31) / 32;
+  // launch shape: threads per CTA, ring depth, prefetch distance, CTAs per SM
+  int threads = 288, stages = 2, dist = 1, per_sm = 2;
+  {
+    static int cfg[4] = {-1, 0, 0, 0};
+    if (cfg[0] < 0) {
+      const char* e = getenv("VATS_PREFILL_SHORT_CFG");  // tuning knob: "threads,stages,dist,ctas_per_sm"
+      if (!e || sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]) != 4) cfg[0] = 0;
+    }
+    if (cfg[0] > 0) {
+      threads = cfg[0]; stages = cfg[1]; dist = cfg[2]; per_sm = cfg[3];
+    }
+  }
+  if (threads != 160 && threads != 288) threads = 288;   // 4 or 8 compute warps + the data-movement warp
+  const int cwarps = threads / 32 - 1;
+  if (per_sm < 1 || per_sm > 2) per_sm = 2;
+  if (stages > vats::kShortMaxStages) stages = vats::kShortMaxStages;
+  auto fits = [&](int st_, int per) {
+    return vats::short_smem_bytes(P.q_words, P.kv_words, P.vt_words, st_, cwarps) <= (size_t)(227 * 1024) / per - 1024;
+  };
+  if (!fits(2, per_sm)) per_sm = 1;   // large sequences: one CTA per SM
+  while (stages > 2 && !fits(stages, per_sm)) --stages;
+  if (stages < 2 || !fits(stages, per_sm)) return -1;
+  if (dist >= stages) dist = stages - 1;
+  if (dist < 1) dist = 1;
+  P.stages = stages;
+  P.dist = dist;
+  const size_t smem = vats::short_smem_bytes(P.q_words, P.kv_words, P.vt_words, stages, cwarps);
+  P.no_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
+  vats::tc_find_divisor((unsigned)A.H, P.div_H);
+  vats::tc_find_divisor((unsigned)A.G, P.div_G);
+  vats::tc_find_divisor((unsigned)hpg, P.div_hpg);
+  vats::tc_find_divisor((unsigned)P.m_blocks, P.div_mb);
+  vats::tc_find_divisor((unsigned)P.hd2, P.div_hd2);
+  int grid = per_sm * sm_count();
+  if (grid > A.N) grid = A.N;
+  P.trace = g_trace;
+  P.trace_cap = g_trace_cap;
+#define VATS_SHORT_LAUNCH(K, B)                                                                                    \
+  {                                                                                                                \
+    static thread_local size_t set = 0;                                                                            \
+    if (smem > set) {                                                                                              \
+      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_short_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                   \
+      set = smem;                                                                                                  \
+    }                                                                                                              \
+    vats::prefill_short_kernel<K, B><<<(unsigned)grid, threads, smem, st>>>(P);                                    \
+  }
+#define VATS_SHORT_CASE(K)               \
+  if (kmax == K) {                       \
+    if (bulk) VATS_SHORT_LAUNCH(K, true) \
+    else VATS_SHORT_LAUNCH(K, false)     \
+  }
+  VATS_SHORT_CASE(8)
+  VATS_SHORT_CASE(16)
+  VATS_SHORT_CASE(32)
+#undef VATS_SHORT_CASE
+#undef VATS_SHORT_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return VATS_OK;
+}
+
 int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   vats::TcParams P;
   std::memset(&P, 0, sizeof(P));
@@ -333,7 +440,10 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
                   A.hd);
     return launch_tc(A, pl, st);
   }
-  if (kernel == VATS_KERNEL_SIMT) return launch_simt(A, st);
+  if (kernel == VATS_KERNEL_SIMT) {
+    const int rc = launch_short(A, st);
+    return rc >= 0 ? rc : launch_simt(A, st);
+  }
   return fail(VATS_ERR_INVALID_ARGUMENT, "unknown kernel selector %d", kernel);
 }
 
