@@ -45,6 +45,7 @@ struct TcParams {
   int q_blocks;      // ceil(Tq / 128)
   int pairs;         // ceil(hpg / 2) head pairs per KV group
   int nk, nv;        // ring depths
+  int ldg_vec;       // kLdg staging: 32-bit words per cp.async copy (2 when every q/k/v row is 8-byte aligned, else 1)
   int o_vec16;       // 1: O rows may be written with 16-byte stores
   int o_stage;       // O write-out: 0 = per-thread row stores; 1 = per-warp shared-memory staging + TMA tile stores
                      // (tmap_o is valid); 2 = the same staging, written out with coalesced 32-bit stores (rows only
@@ -79,47 +80,41 @@ __host__ __device__ inline size_t tc_smem_bytes(int regions, int nk, int nv, int
 }
 
 // Stage rows [row0, row0+128) x hd of a row-strided bf16 matrix into a 128B-swizzled K-major tile (the layout a
-// (64 x 128) SWIZZLE_128B TMA box would produce), with 32-bit loads.  Rows >= T and columns [hd, hd_pad) are zero.
-template <int NT>
-__device__ __forceinline__ void ldg_stage_tile(unsigned char* dst, const __nv_bfloat16* src, long long stride_t,
-                                               int row0, int T, int hd, int hd_pad, int tid) {
-  const int wpr = hd_pad >> 1;  // 32-bit words per staged row
-  const int hw = hd >> 1;       // valid words per row
-  // word index idx = r * wpr + w walks tid, tid + NT, ...; (r, w) advance incrementally (no per-word division)
-  const int dq = NT / wpr, dr = NT % wpr;
-  int r_l = tid / wpr, w_l = tid - r_l * wpr;  // load cursor
-  int r_s = r_l, w_s = w_l;                    // store cursor
-  constexpr int UNR = 8;
-  while (r_s < 128) {
-    uint32_t val[UNR];
-#pragma unroll
-    for (int i = 0; i < UNR; ++i) {
-      val[i] = 0u;
-      if (r_l < 128 && (row0 + r_l) < T && w_l < hw)
-        val[i] = ptx::ldg_nc_u32(src + (long long)(row0 + r_l) * stride_t + 2 * w_l);
-      w_l += dr;
-      r_l += dq;
-      if (w_l >= wpr) {
-        w_l -= wpr;
-        ++r_l;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < UNR; ++i) {
-      if (r_s < 128) {
-        const uint32_t r = (uint32_t)r_s, w = (uint32_t)w_s;
-        const uint32_t wi = w & 31u;
-        const uint32_t off = (w >> 5) * kTcRegionBytes + r * 128u + (((wi >> 2) ^ (r & 7u)) << 4) + ((wi & 3u) << 2);
-        *reinterpret_cast<uint32_t*>(dst + off) = val[i];
-      }
-      w_s += dr;
-      r_s += dq;
-      if (w_s >= wpr) {
-        w_s -= wpr;
-        ++r_s;
-      }
+// (64 x 128) SWIZZLE_128B TMA box would produce) with asynchronous 4- or 8-byte copies (cp.async, LDGSTS): nothing is
+// staged through registers, so a loader thread keeps a whole tile (and the next one) in flight.  Rows >= T and
+// columns [hd, hd_pad) are zero-filled (src-size 0).  VW = 32-bit words per copy: 2 when rows are 8-byte aligned.
+// The caller commits the group and, once it has landed, makes it visible to the async proxy before signalling.
+template <int NT, int VW>
+__device__ __forceinline__ void cpasync_stage_tile(uint32_t dst, const __nv_bfloat16* src, long long stride_t, int row0,
+                                                   int T, int hd, int hd_pad, int tid) {
+  const int upr = hd_pad / (2 * VW);  // copy units per staged row
+  const int hu = hd / (2 * VW);       // valid units per row
+  // unit index idx = r * upr + u walks tid, tid + NT, ...; (r, u) advance incrementally (no per-copy division)
+  const int dq = NT / upr, dr = NT % upr;
+  int r = tid / upr, u = tid - r * upr;
+  while (r < 128) {
+    const bool ok = (row0 + r) < T && u < hu;
+    const __nv_bfloat16* g = ok ? src + (long long)(row0 + r) * stride_t + 2 * VW * u : src;
+    const uint32_t w = (uint32_t)(u * VW);   // first 32-bit word of the unit within the row
+    const uint32_t wi = w & 31u;
+    const uint32_t off = (w >> 5) * kTcRegionBytes + (uint32_t)r * 128u + (((wi >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((wi & 3u) << 2);
+    const uint32_t nbytes = ok ? 4u * VW : 0u;
+    if (VW == 2)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + off), "l"(g), "r"(nbytes) : "memory");
+    else
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + off), "l"(g), "r"(nbytes) : "memory");
+    u += dr;
+    r += dq;
+    if (u >= upr) {
+      u -= upr;
+      ++r;
     }
   }
+}
+__device__ __forceinline__ void cpasync_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpasync_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <int N>
@@ -323,12 +318,26 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         }
       }
     } else {
-      // ---- LDG staging: 96 threads copy each K / V tile into the swizzled layout
+      // ---- cp.async staging: 96 threads copy each K / V tile into the swizzled layout.  A thread signals a tile
+      //      (wait_group -> fence.proxy.async -> arrive) only after issuing the copies of the next one, so two tiles
+      //      are in flight per thread.
       const int ltid = threadIdx.x - 8 * 32;
-      unsigned char* sK_g = smem_raw + (sK - raw);
-      unsigned char* sV_g = smem_raw + (sV - raw);
       int ks = 0, vs = 0;
       uint32_t kph = 0u, vph = 0u;
+      uint32_t pending = 0u;   // full barrier of the tile whose copies were committed last (0 = none)
+      auto stage = [&](uint32_t dst, const __nv_bfloat16* base_ptr, long long stride_t, int k0, uint32_t full_bar) {
+        if (P.ldg_vec == 2)
+          cpasync_stage_tile<kTcLoaderThreads, 2>(dst, base_ptr, stride_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+        else
+          cpasync_stage_tile<kTcLoaderThreads, 1>(dst, base_ptr, stride_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
+        cpasync_commit();
+        if (pending != 0u) {
+          cpasync_wait<1>();
+          fence_proxy_async_smem();
+          mbar_arrive(pending);
+        }
+        pending = full_bar;
+      };
       for (int w = blockIdx.x; w < P.num_work; w += gridDim.x) {
         const TcWork wk = tc_decode_work(P, w);
         if (wk.n_tiles <= 0) continue;
@@ -336,21 +345,18 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         const __nv_bfloat16* vbase = a.v + wk.n * a.vs_n + (long long)wk.g * a.vs_h;
         for (int j = 0; j < wk.n_tiles; ++j) {
           const int k0 = (wk.t_first + j) * kTcBlockN;
-          {
-            mbar_wait(smem_u32(&bars->k_empty[ks]), kph ^ 1u);
-            ldg_stage_tile<kTcLoaderThreads>(sK_g + (size_t)ks * tile_bytes, kbase, a.ks_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
-            fence_proxy_async_smem();
-            mbar_arrive(smem_u32(&bars->k_full[ks]));
-            if (++ks == P.nk) { ks = 0; kph ^= 1u; }
-          }
-          {
-            mbar_wait(smem_u32(&bars->v_empty[vs]), vph ^ 1u);
-            ldg_stage_tile<kTcLoaderThreads>(sV_g + (size_t)vs * tile_bytes, vbase, a.vs_t, k0, a.Tk, a.hd, P.hd_pad, ltid);
-            fence_proxy_async_smem();
-            mbar_arrive(smem_u32(&bars->v_full[vs]));
-            if (++vs == P.nv) { vs = 0; vph ^= 1u; }
-          }
+          mbar_wait(smem_u32(&bars->k_empty[ks]), kph ^ 1u);
+          stage(sK + (uint32_t)ks * tile_bytes, kbase, a.ks_t, k0, smem_u32(&bars->k_full[ks]));
+          if (++ks == P.nk) { ks = 0; kph ^= 1u; }
+          mbar_wait(smem_u32(&bars->v_empty[vs]), vph ^ 1u);
+          stage(sV + (uint32_t)vs * tile_bytes, vbase, a.vs_t, k0, smem_u32(&bars->v_full[vs]));
+          if (++vs == P.nv) { vs = 0; vph ^= 1u; }
         }
+      }
+      if (pending != 0u) {
+        cpasync_wait<0>();
+        fence_proxy_async_smem();
+        mbar_arrive(pending);
       }
     }
   } else {
@@ -518,7 +524,12 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         // the 128 threads of this warpgroup stage their own Q tile, once the previous item's MMAs are done with it
         mbar_wait(smem_u32(&bars->q_empty[t]), (qn & 1u) ^ 1u);
         const __nv_bfloat16* qbase = a.q + n * a.qs_n + (long long)head * a.qs_h;
-        ldg_stage_tile<128>(smem_raw + (sQ - raw) + (size_t)t * tile_bytes, qbase, a.qs_t, q0, a.Tq, a.hd, P.hd_pad, r);
+        if (P.ldg_vec == 2)
+          cpasync_stage_tile<128, 2>(sQ + (uint32_t)t * tile_bytes, qbase, a.qs_t, q0, a.Tq, a.hd, P.hd_pad, r);
+        else
+          cpasync_stage_tile<128, 1>(sQ + (uint32_t)t * tile_bytes, qbase, a.qs_t, q0, a.Tq, a.hd, P.hd_pad, r);
+        cpasync_commit();
+        cpasync_wait<0>();
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bars->q_fixed[t]));
       }

@@ -337,6 +337,12 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.pairs = (P.a.hpg + 1) / 2;
   // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  {
+    auto al8 = [&](const void* ptr, const int64_t* st3) {
+      return (reinterpret_cast<uintptr_t>(ptr) & 7u) == 0 && st3[0] % 4 == 0 && st3[1] % 4 == 0 && st3[2] % 4 == 0;
+    };
+    P.ldg_vec = (A.hd % 4 == 0 && al8(A.q, A.qs) && al8(A.k, A.ks) && al8(A.v, A.vs)) ? 2 : 1;
+  }
   P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1

@@ -57,7 +57,7 @@ def apply_qk_norm(query: torch.Tensor, key: torch.Tensor) -> Tuple[torch.Tensor,
     return F.normalize(query, p=2, dim=-1, eps=1e-6), F.normalize(key, p=2, dim=-1, eps=1e-6)
 
 
-def _to_kernel_layout(x: torch.Tensor) -> torch.Tensor:
+def _to_kernel_layout(x: torch.Tensor, pad: bool = True) -> torch.Tensor:
     """bf16 copy of a [N, T, heads, hd] tensor in a TMA-addressable layout.
 
     The cast to bf16 writes a new tensor anyway; for head dims that are not a multiple of 8 (60, 66) it is written
@@ -66,8 +66,8 @@ def _to_kernel_layout(x: torch.Tensor) -> torch.Tensor:
     padding is never read (the tensor map's inner extent is hd) and costs no extra pass over the data.
     """
     hd = x.size(-1)
-    if hd % 8 == 0:
-        return x.to(torch.bfloat16)
+    if hd % 8 == 0 or not pad:
+        return x.to(torch.bfloat16).contiguous()
     hd8 = (hd + 7) // 8 * 8
     buf = torch.empty(*x.shape[:-1], hd8, dtype=torch.bfloat16, device=x.device)
     view = buf[..., :hd]
@@ -84,6 +84,9 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: 
     to bf16 (the kernels' arithmetic type: bf16 operands, fp32 accumulation) and the result is cast back.
     """
     out_dtype = out_dtype or q.dtype
-    o = ops.gqa_swa_prefill(_to_kernel_layout(q), _to_kernel_layout(k), _to_kernel_layout(v), q_valid, k_valid,
-                            float(scale), bool(causal), int(left), int(right))
+    # sequences of at most 32 keys go to the one-CTA-per-sequence kernel, which streams dense [T, heads, hd] blocks
+    # with bulk copies: no head-stride padding there
+    pad = k.size(1) > 32
+    o = ops.gqa_swa_prefill(_to_kernel_layout(q, pad), _to_kernel_layout(k, pad), _to_kernel_layout(v, pad), q_valid,
+                            k_valid, float(scale), bool(causal), int(left), int(right))
     return o.to(out_dtype)
