@@ -365,6 +365,34 @@ def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool, layout:
         t1 = time.perf_counter()
         res["ms_compute_plus_allgather"] = max_over_ranks((t1 - t0) / steps * 1e3, world)
         del full
+        # the same, cut into 4 pieces whose gathers run on a side stream under the next piece's kernel
+        core = lambda q_, k_, v_, qv_, kv_, causal=False: ops.gqa_swa_prefill(
+            q_, k_, v_, qv_, kv_, scale, causal, c["left"], 0 if causal else -1, 0)
+        for _ in range(2):
+            full = sharding.local_attention_gather(core, q, k, v, N, H, G, chunks=4, causal=c["causal"])
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            full = sharding.local_attention_gather(core, q, k, v, N, H, G, chunks=4, causal=c["causal"])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        res["ms_compute_plus_allgather_overlapped"] = max_over_ranks((t1 - t0) / steps * 1e3, world)
+        del full
+        # ... and with copy-engine peer writes into symmetric memory instead of NCCL (needs no SM: really overlaps)
+        try:
+            pg = sharding.PeerGather(N, T, H, hd, torch.bfloat16, dev)
+            for _ in range(2):
+                full = sharding.local_attention_gather(core, q, k, v, N, H, G, chunks=4, causal=c["causal"], peer=pg)
+            barrier_sync(world)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                full = sharding.local_attention_gather(core, q, k, v, N, H, G, chunks=4, causal=c["causal"], peer=pg)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            res["ms_compute_plus_peer_gather_overlapped"] = max_over_ranks((t1 - t0) / steps * 1e3, world)
+            del full, pg
+        except Exception as e:
+            res["peer_gather_error"] = f"{type(e).__name__}: {e}"
     units = world if (not shard) else 1  # unsharded workloads are replicated per rank (weak)
     fl = prefill_flops(c) * units
     by = prefill_bytes(c) * units

@@ -59,12 +59,21 @@ def _worker(rank, world, port, B, G, H, results):
         s = sharding.partition(B, G, world, rank)
         hpg = H // G
         ok = ok and torch.allclose(local, full[s.b0:s.b1, :, s.g0 * hpg:s.g1 * hpg], atol=1e-6)
+        # chunked (overlappable) gather: batch pieces when a rank owns >= 2 sequences, token pieces for one causal
+        # sequence per rank, plain gather otherwise — always the same values
+        for chunks in (2, 3):
+            out_c = sharding.sharded_attention(core, q, k, v, k_valid=kvalid, chunks=chunks, **kw)
+            ok = ok and torch.allclose(out_c, full, atol=1e-6)
+        # chunked prefill against a longer key range (Tq < Tk, bottom-right aligned)
+        full2 = core(q[:, 4:], k, v, None, kvalid, **kw)
+        out2 = sharding.sharded_attention(core, q[:, 4:], k, v, k_valid=kvalid, chunks=2, **kw)
+        ok = ok and torch.allclose(out2, full2, atol=1e-6)
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B,G,H", [(4, 2, 4), (3, 2, 6), (1, 4, 8)])
+@pytest.mark.parametrize("B,G,H", [(4, 2, 4), (3, 2, 6), (1, 4, 8), (2, 2, 4)])
 def test_sharded_equals_unsharded_world2(B, G, H):
     world = 2
     mgr = mp.Manager()

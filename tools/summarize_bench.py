@@ -7,6 +7,12 @@ for k, v in d.get("other_workloads", {}).items():
         print(k, "ERROR", v["error"]); continue
     rf = v["roofline"]
     extra = f" +allgather {v['ms_compute_plus_allgather']:.3f} ms" if "ms_compute_plus_allgather" in v else ""
+    if "ms_compute_plus_allgather_overlapped" in v:
+        extra += f" (overlapped {v['ms_compute_plus_allgather_overlapped']:.3f} ms)"
+    if "ms_compute_plus_peer_gather_overlapped" in v:
+        extra += f" (peer writes {v['ms_compute_plus_peer_gather_overlapped']:.3f} ms)"
+    if "peer_gather_error" in v:
+        extra += " peer_gather_error=" + v["peer_gather_error"][:80]
     print(f"{k:26s} {v['ms_compute']:.4f} ms  {v['tflops']:8.1f} TFLOP/s {v['gbs']:8.1f} GB/s  {rf['bound']} frac={100*rf['frac']:.1f}%{extra}")
 if d.get("cpu_baseline"): print("cpu_baseline", d["cpu_baseline"])
 print("clocks", d.get("clocks"))
