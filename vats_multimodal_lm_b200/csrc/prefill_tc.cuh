@@ -675,36 +675,35 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
         // rows >= Tq and columns >= hd) or, when O rows are only 4-byte aligned, with coalesced 32-bit stores.
         const uint32_t stage = sO + (uint32_t)warp * kTcOStageBytes;
         const int row_w = q0 + (warp & 3) * 32;  // first token of this warp's 32 rows
-#pragma unroll 1
-        for (int cb = 0; cb < P.hd_pad; cb += 64) {
+        // the whole accumulator row leaves TMEM in one batch of loads (one wait), and the accumulator is handed back
+        // to the MMA warp before anything is written out
+        uint32_t acc[128];
+#pragma unroll
+        for (int pc16 = 0; pc16 < 8; ++pc16) tmem_ld_32x32b_x16(tO + pc16 * 16, acc + pc16 * 16);   // (all 128 columns of
+        tmem_ld_wait();                                       // the tile's O region exist; those >= hd_pad are never stored)
+        if (n_tiles > 0) {
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->o_empty[t]));
+          ++qn;
+        }
+        const bool have = n_tiles > 0;   // an item with nothing to attend writes zeros (TMEM then holds stale values)
+#pragma unroll
+        for (int cbi = 0; cbi < 2; ++cbi) {
+          const int cb = cbi * 64;
+          if (cb >= P.hd_pad) continue;
           // the previous store of this warp must have finished reading the staging tile
           if (P.o_stage == 1 && lane == 0) bulk_wait_group_read0();
           __syncwarp();
-#pragma unroll 1
-          for (int c = cb; c < cb + 64 && c < P.hd_pad; c += 32) {   // 32 accumulator columns at a time
-            uint32_t tmp[32];
-            if (n_tiles > 0) {
-              tmem_ld_32x32b_x16(tO + c, tmp);
-              if (c + 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + c + 16, tmp + 16);
-              tmem_ld_wait();
-              if (c + 32 >= P.hd_pad) {   // last chunk is out of TMEM: hand the accumulator back
-                tc_fence_before();
-                mbar_arrive(smem_u32(&bars->o_empty[t]));
-                ++qn;
-              }
-            } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) tmp[i] = 0u;
-            }
-            const uint32_t u0 = (uint32_t)(c - cb) >> 3;   // first 16-byte unit of this chunk within the 128-byte row
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t x = pack_bf16x2(__uint_as_float(tmp[8 * i + 0]) * inv, __uint_as_float(tmp[8 * i + 1]) * inv);
-              const uint32_t y = pack_bf16x2(__uint_as_float(tmp[8 * i + 2]) * inv, __uint_as_float(tmp[8 * i + 3]) * inv);
-              const uint32_t z = pack_bf16x2(__uint_as_float(tmp[8 * i + 4]) * inv, __uint_as_float(tmp[8 * i + 5]) * inv);
-              const uint32_t w = pack_bf16x2(__uint_as_float(tmp[8 * i + 6]) * inv, __uint_as_float(tmp[8 * i + 7]) * inv);
-              const uint32_t dst = stage + (uint32_t)lane * 128u + (((u0 + i) ^ ((uint32_t)lane & 7u)) << 4);
-              // (columns >= hd_pad of the last chunk hold stale accumulator words; TMA clips everything >= hd)
+          for (int u = 0; u < 8; ++u) {
+            if (cb + u * 8 < P.hd_pad) {
+              uint32_t x = pack_bf16x2(__uint_as_float(acc[cb + 8 * u + 0]) * inv, __uint_as_float(acc[cb + 8 * u + 1]) * inv);
+              uint32_t y = pack_bf16x2(__uint_as_float(acc[cb + 8 * u + 2]) * inv, __uint_as_float(acc[cb + 8 * u + 3]) * inv);
+              uint32_t z = pack_bf16x2(__uint_as_float(acc[cb + 8 * u + 4]) * inv, __uint_as_float(acc[cb + 8 * u + 5]) * inv);
+              uint32_t w = pack_bf16x2(__uint_as_float(acc[cb + 8 * u + 6]) * inv, __uint_as_float(acc[cb + 8 * u + 7]) * inv);
+              if (!have) x = y = z = w = 0u;
+              const uint32_t dst = stage + (uint32_t)lane * 128u + (((uint32_t)u ^ ((uint32_t)lane & 7u)) << 4);
+              // (columns >= hd_pad of the last chunk are never written; TMA clips everything >= hd)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
             }
           }
