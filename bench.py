@@ -259,22 +259,26 @@ def bench_decode(args, world, peaks):
     value = world * nbytes / (wall / args.steps) / 1e9
     achieved = nbytes / (dev_ms * 1e-3) / 1e9
 
-    # ---- end to end through the public op with HOST buffers: H2D of the step's q and new k/v (pinned), cache
-    #      append, decode, D2H of the result, every step
+    # ---- end to end through the public ops with HOST buffers: H2D of the step's projected q and new k/v (pinned),
+    #      fused qk-norm + RoPE + cache append (vats::decode_prepare), decode, D2H of the result, every step
     qh = q.cpu().pin_memory()
     knh = kc[:, S - 1].cpu().pin_memory()
     vnh = vc[:, S - 1].cpu().pin_memory()
     lens_h = lens.cpu().pin_memory()
     oh = torch.empty((B, H, hd), dtype=torch.bfloat16).pin_memory()
 
+    pos = torch.arange(S, dtype=torch.float32, device=dev)
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.float32, device=dev) / hd))
+    cos_t, sin_t = torch.cos(torch.outer(pos, inv_freq)), torch.sin(torch.outer(pos, inv_freq))
+
     def e2e_step():
         qd = qh.to(dev, non_blocking=True)
         kn = knh.to(dev, non_blocking=True)
         vn = vnh.to(dev, non_blocking=True)
         ld = lens_h.to(dev, non_blocking=True)
-        kc[:, S - 1] = kn      # append the new token's k/v at position seq_len-1
-        vc[:, S - 1] = vn
-        o = ops.gqa_swa_decode(qd, kc, vc, ld, scale, left)
+        # L2-normalise + rotate q and k at position seq_len-1, append k/v there (one launch), then attend
+        qr = ops.decode_prepare(qd, kn, vn, kc, vc, ld, cos_t, sin_t, True, 1e-6)
+        o = ops.gqa_swa_decode(qr, kc, vc, ld, scale, left)
         oh.copy_(o, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -286,9 +290,50 @@ def bench_decode(args, world, peaks):
         e2e_step()
     t1 = time.perf_counter()
     barrier_sync(world)
-    clocks = sampler.stop()   # sampled over the device-timed region and the end-to-end region (both under load)
     e2e_wall = max_over_ranks(t1 - t0, world)
-    e2e_value = world * nbytes / (e2e_wall / args.steps) / 1e9
+    e2e_eager = world * nbytes / (e2e_wall / args.steps) / 1e9
+
+    # the same step captured once in a CUDA graph (pinned H2D copies, the two kernels, the D2H copy) and replayed:
+    # one launch per step instead of six plus the Python op overhead
+    e2e_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            def body():
+                qd = qh.to(dev, non_blocking=True)
+                kn = knh.to(dev, non_blocking=True)
+                vn = vnh.to(dev, non_blocking=True)
+                ld = lens_h.to(dev, non_blocking=True)
+                qr = ops.decode_prepare(qd, kn, vn, kc, vc, ld, cos_t, sin_t, True, 1e-6)
+                o = ops.gqa_swa_decode(qr, kc, vc, ld, scale, left)
+                oh.copy_(o, non_blocking=True)
+            for _ in range(2):
+                body()
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ref_o = oh.clone()
+        for _ in range(3):
+            graph.replay()
+            torch.cuda.synchronize()
+        if not torch.equal(ref_o, oh):
+            raise RuntimeError("graph replay does not reproduce the eager step")
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            graph.replay()
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier_sync(world)
+        e2e_graph = world * nbytes / (max_over_ranks(t1 - t0, world) / args.steps) / 1e9
+    except Exception as e:   # the eager number stands
+        sys.stderr.write(f"bench: CUDA-graph e2e skipped ({type(e).__name__}: {e})\n")
+    clocks = sampler.stop()   # sampled over the device-timed region and the end-to-end region (both under load)
+    e2e_value = e2e_graph if e2e_graph is not None else e2e_eager
     h2d = qh.numel() * 2 + knh.numel() * 2 + vnh.numel() * 2 + lens_h.numel() * 4
     d2h = oh.numel() * 2
 
@@ -304,8 +349,10 @@ def bench_decode(args, world, peaks):
         value=value, ms_per_step=wall / args.steps * 1e3, dev_ms=dev_ms_max, clocks=clocks,
         launches=launches_per_step * args.steps,
         e2e=dict(value=e2e_value, unit="GB/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                 mode="cuda_graph_replay" if e2e_graph is not None else "eager", eager_value=e2e_eager,
                  note="KV cache is resident state (it never leaves HBM between steps); the step's inputs are the new "
-                      "token's q/k/v"),
+                      "token's projected q/k/v: H2D, vats::decode_prepare (qk-norm + RoPE + cache append, one "
+                      "launch), vats::gqa_swa_decode, D2H"),
         roofline=dict(bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                       frac=achieved / peaks["hbm_gbs"], traffic=traffic,
                       peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",

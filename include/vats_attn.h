@@ -13,6 +13,7 @@
  *                            src/transformers/vision/vit_3d/optimized_attention.py:185-348   (_grouped_query_attention, spatial and temporal)
  *   vats_attn_decode         src/optimized_attention.py:508-516 + 709-714  (the intended KV-cache single-query step; the cache
  *                                                                           type is KVCache, src/optimized_attention.py:169-287)
+ *   vats_attn_decode_prepare src/optimized_attention.py:463-474 + 224-257  (qk-norm, RoPE and cache append of the new token, fused)
  *   vats_attn_debug_mask     the mask predicate of SURVEY.md §8a-0 (src/optimized_attention.py:519-520, 632-634, 673-675;
  *                            vit_3d/optimized_attention.py:276-277) materialised for bit-exact tests
  *
@@ -111,6 +112,28 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
                      void* workspace, size_t workspace_bytes, void* stream);
 
 size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left);
+
+/*
+ * Pre-core step of one cached decode token, fused into one launch (decode part):
+ *     q, k = F.normalize(q, eps), F.normalize(k, eps)     utils/attention_utils.py:80-102   (only if qk_norm != 0)
+ *     q, k = rope(q), rope(k)  at position seq_lens[b]-1  src/optimized_attention.py:97-143 (interleaved pairs 2i, 2i+1;
+ *                                                         cos/sin tables as built by RoPE._update_cache :83-99)
+ *     append k, v to the cache at that position           src/optimized_attention.py:224-257 (intended contract)
+ * fp32 arithmetic, one rounding to bf16 at the end.  The order (norm, then RoPE) is src/optimized_attention.py:467-474.
+ *
+ *   q_in [B,H,hd], k_in / v_in [B,G,hd]   bf16 (in_dtype 0) or fp32 (in_dtype 1); strides (batch, head) in elements
+ *   q_out [B,H,hd] bf16;   k_cache / v_cache [B,S_max,G,hd] bf16, strides (batch, token, head)
+ *   seq_lens [B] int32: cache length INCLUDING the token being written (the same array vats_attn_decode takes);
+ *             sequences with seq_lens[b] <= 0 or > S_max are skipped
+ *   cos_table / sin_table [>= max position + 1, hd/2] fp32, or both NULL for no rotation
+ */
+int vats_attn_decode_prepare(const void* q_in, const void* k_in, const void* v_in, int in_dtype,
+                             void* q_out, void* k_cache, void* v_cache, const int32_t* seq_lens,
+                             const float* cos_table, const float* sin_table,
+                             int B, int H, int G, int hd, int S_max,
+                             const int64_t qin_strides[2], const int64_t kin_strides[2], const int64_t vin_strides[2],
+                             const int64_t qout_strides[2], const int64_t k_strides[3], const int64_t v_strides[3],
+                             int qk_norm, float eps, void* stream);
 
 /* Number of kernels the last successful vats_attn_decode / vats_attn_prefill on this thread launched. */
 int vats_attn_last_launch_count(void);

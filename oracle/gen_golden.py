@@ -92,8 +92,32 @@ def vit3d_case(name, seed, d_model, H, G, grid, B, pad):
     print(name, tuple(out.shape), len(calls), "sdpa call(s)")
 
 
+def prepare_case(name, seed, H, G, hd, theta, P, B, use_qk_norm=True):
+    """Pre-core producers of the LLM module (src/optimized_attention.py:463-474): apply_qk_norm then RoPE, run by the
+    reference on a [B, P+1, heads, hd] tensor; the fixture keeps the LAST position (index P) — what a cached decode
+    step has to produce for its new token — plus the cos / sin rows the reference used."""
+    m = ref.llm()
+    from utils.attention_utils import apply_qk_norm
+    torch.manual_seed(seed)
+    rope = m.RoPE(hd, theta)
+    q = torch.randn(B, P + 1, H, hd)
+    k = torch.randn(B, P + 1, G, hd)
+    with torch.no_grad():
+        qn, kn = apply_qk_norm(q, k) if use_qk_norm else (q, k)
+        qr, kr = rope(qn), rope(kn)
+    torch.save({
+        "kind": "prepare", "H": H, "G": G, "hd": hd, "theta": theta, "position": P, "use_qk_norm": use_qk_norm,
+        "q_in": q[:, P].clone(), "k_in": k[:, P].clone(), "q_out": qr[:, P].clone(), "k_out": kr[:, P].clone(),
+        "cos_row": rope.cos_cache[P].clone(), "sin_row": rope.sin_cache[P].clone(),
+    }, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(qr[:, P].shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    # pre-core step of a decode token (qk-norm + RoPE at position P)
+    prepare_case("prepare_hd128_p300", 401, 8, 2, 128, 10000.0, 300, 3)
+    prepare_case("prepare_hd60_p17_nonorm", 402, 6, 2, 60, 10000.0, 17, 2, use_qk_norm=False)
     # LLM — xsmall-like geometry (hd = 16, softmax_scale = sqrt(16) as in model_args_xsmall.py:31)
     llm_case("llm_hd16_causal", 101, 64, 4, 2, 10000.0, 4.0, 2, 16, 128, 0, True, False)
     llm_case("llm_hd16_causal_pad", 102, 64, 4, 2, 10000.0, 4.0, 3, 16, 128, 0, True, True)

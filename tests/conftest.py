@@ -25,7 +25,12 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt"))
+    """Module-level fixtures (reference module run + captured SDPA calls); the prepare_* fixtures are listed apart."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith("prepare_"))
+
+
+def prepare_golden_files():
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith("prepare_"))
 
 
 def load_golden(name):

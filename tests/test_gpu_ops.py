@@ -310,3 +310,64 @@ def test_decode_stale_rows_past_sequence_end_do_not_leak():
         vd[b, L:] = float("nan")
     o = ops.gqa_swa_decode(q.cuda(), kd.cuda(), vd.cuda(), lens.cuda(), 0.09, -1)
     check_close(o, decode_explicit(q, kc, vc, lens, 0.09, -1), "stale rows")
+
+
+# ---- fused decode pre-core step (qk-norm + RoPE + cache append), SURVEY §8f rank 1
+from conftest import load_golden, prepare_golden_files  # noqa: E402
+from oracle import decode_prepare_explicit, rope_tables  # noqa: E402
+
+
+@pytest.mark.parametrize("name", prepare_golden_files())
+def test_decode_prepare_matches_reference_fixture(name):
+    """The kernel against what the unmodified reference produced (apply_qk_norm + RoPE at position P)."""
+    fx = load_golden(name)
+    P, hd, G, H = fx["position"], fx["hd"], fx["G"], fx["H"]
+    B = fx["q_in"].size(0)
+    cos, sin = rope_tables(hd, fx["theta"], P + 8)
+    kc = torch.zeros(B, P + 8, G, hd, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    lens = torch.full((B,), P + 1, dtype=torch.int32, device="cuda")
+    v_in = torch.randn(B, G, hd, generator=torch.Generator().manual_seed(5))
+    q_out = ops.decode_prepare(fx["q_in"].cuda(), fx["k_in"].cuda(), v_in.cuda(), kc, vc, lens, cos.cuda(), sin.cuda(),
+                               fx["use_qk_norm"], 1e-6)
+    torch.cuda.synchronize()
+    # one bf16 rounding of fp32 values: relative error <= 2^-8
+    assert torch.allclose(q_out.float().cpu(), fx["q_out"], atol=4e-3 * fx["q_out"].abs().max().item(), rtol=4e-3)
+    assert torch.equal(q_out.cpu(), fx["q_out"].bfloat16()) or \
+        (q_out.float().cpu() - fx["q_out"]).abs().max() <= 2 ** -8 * fx["q_out"].abs().max()
+    assert (kc[:, P].float().cpu() - fx["k_out"]).abs().max() <= 2 ** -8 * fx["k_out"].abs().max()
+    assert torch.equal(vc[:, P].cpu(), v_in.bfloat16())
+    assert torch.count_nonzero(kc[:, :P]) == 0 and torch.count_nonzero(kc[:, P + 1:]) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B,H,G,hd,S", [(5, 32, 8, 128, 600), (3, 24, 8, 60, 97), (4, 6, 6, 66, 40), (2, 8, 1, 256, 33)])
+def test_decode_prepare_matches_oracle_and_feeds_decode(B, H, G, hd, S, dtype):
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(B, H, hd, generator=g).to(dtype)
+    k = torch.randn(B, G, hd, generator=g).to(dtype)
+    v = torch.randn(B, G, hd, generator=g).to(dtype)
+    kc = torch.nn.functional.normalize(torch.randn(B, S, G, hd, generator=g), dim=-1).bfloat16()
+    vc = torch.randn(B, S, G, hd, generator=g).bfloat16()
+    lens = torch.randint(1, S + 1, (B,), generator=g).int()
+    lens[0] = S          # last slot
+    lens[-1] = 0         # empty sequence: nothing is written
+    cos, sin = rope_tables(hd, 10000.0, S)
+    dk, dv = kc.cuda().clone(), vc.cuda().clone()
+    q_out = ops.decode_prepare(q.cuda(), k.cuda(), v.cuda(), dk, dv, lens.cuda(), cos.cuda(), sin.cuda(), True, 1e-6)
+    torch.cuda.synchronize()
+    q_ref, k_ref, v_ref = decode_prepare_explicit(q, k, v, kc, vc, lens, cos, sin, True)
+    live = lens > 0
+    assert (q_out.float().cpu()[live] - q_ref[live]).abs().max() <= 2 ** -8 + 1e-6   # |q| <= 1 after the norm
+    assert (dk.float().cpu() - k_ref).abs().max() <= 2 ** -8 + 1e-6
+    assert torch.equal(dv.cpu(), v_ref.bfloat16())
+    # the decode kernel consumes what the prepare kernel wrote
+    o = ops.gqa_swa_decode(q_out, dk, dv, lens.cuda(), hd ** -0.5, 64)
+    torch.cuda.synchronize()
+    ref = decode_explicit(q_out.cpu(), dk.cpu(), dv.cpu(), lens, hd ** -0.5, 64)
+    check_close(o[live.cuda()], ref[live], "decode after prepare")
+    # no rotation / no norm variants
+    dk2, dv2 = kc.cuda().clone(), vc.cuda().clone()
+    q2 = ops.decode_prepare(q.cuda(), k.cuda(), v.cuda(), dk2, dv2, lens.cuda(), None, None, False, 1e-6)
+    q2_ref, k2_ref, _ = decode_prepare_explicit(q, k, v, kc, vc, lens, None, None, False)
+    assert torch.equal(q2.cpu()[live], q2_ref.bfloat16()[live]) and torch.equal(dk2.cpu(), k2_ref.bfloat16())

@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from conftest import golden_files, load_golden
+from conftest import golden_files, load_golden, prepare_golden_files
 from oracle import expand_kv, mask_predicate, sdpa_explicit
 
 
@@ -111,3 +111,23 @@ def test_predicate_against_python_loops(Tq, Tk, causal, left, right):
                 ok = ok and (left < 0 or j >= i + off - left)
                 ok = ok and (right < 0 or j <= i + off + right)
                 assert bool(m[n, i, j]) == ok
+
+
+@pytest.mark.parametrize("name", prepare_golden_files())
+def test_prepare_oracle_matches_reference_producers(name):
+    """qk-norm + RoPE of the reference (apply_qk_norm, RoPE.forward) at one position == oracle.decode_prepare_explicit,
+    and the oracle's cos/sin tables equal the reference's cache rows bit for bit."""
+    from oracle import decode_prepare_explicit, rope_tables
+    fx = load_golden(name)
+    P, hd, G = fx["position"], fx["hd"], fx["G"]
+    cos, sin = rope_tables(hd, fx["theta"], P + 1)
+    assert torch.equal(cos[P], fx["cos_row"]) and torch.equal(sin[P], fx["sin_row"])
+    B = fx["q_in"].size(0)
+    lens = torch.full((B,), P + 1, dtype=torch.int32)
+    kc = torch.zeros(B, P + 1, G, hd)
+    vc = torch.zeros(B, P + 1, G, hd)
+    v_in = torch.randn(B, G, hd)
+    q_out, kc2, vc2 = decode_prepare_explicit(fx["q_in"], fx["k_in"], v_in, kc, vc, lens, cos, sin, fx["use_qk_norm"])
+    assert torch.allclose(q_out, fx["q_out"], atol=2e-6, rtol=0)
+    assert torch.allclose(kc2[:, P], fx["k_out"], atol=2e-6, rtol=0)
+    assert torch.equal(vc2[:, P], v_in) and torch.count_nonzero(kc2[:, :P]) == 0

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "vats_attn_prefill_plan",
     "vats_attn_decode",
     "vats_attn_decode_workspace_bytes",
+    "vats_attn_decode_prepare",
     "vats_attn_last_launch_count",
     "vats_attn_debug_mask",
     "vats_attn_debug_tile_range",
@@ -77,6 +78,9 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_decode.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, p3, p3, p3, p3, f, i, vp, sz, vp]
         lib.vats_attn_decode_workspace_bytes.restype = sz
         lib.vats_attn_decode_workspace_bytes.argtypes = [i, i, i, i, i, i]
+        lib.vats_attn_decode_prepare.restype = i
+        lib.vats_attn_decode_prepare.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, p3, p3, p3, p3, p3, p3,
+                                                 i, f, vp]
         lib.vats_attn_last_launch_count.restype = i
         lib.vats_attn_last_launch_count.argtypes = []
         lib.vats_attn_debug_mask.restype = i
@@ -138,6 +142,16 @@ def decode(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, seq_lens_ptr: int, B:
         q_ptr, k_ptr, v_ptr, o_ptr, seq_lens_ptr, B, H, G, hd, S_max,
         _i64x2(*q_strides), _i64x3(*k_strides), _i64x3(*v_strides), _i64x2(*o_strides),
         float(scale), int(left), workspace_ptr, workspace_bytes, stream))
+
+
+def decode_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, q_out_ptr: int, k_cache_ptr: int,
+                   v_cache_ptr: int, seq_lens_ptr: int, cos_ptr: Optional[int], sin_ptr: Optional[int], B: int, H: int,
+                   G: int, hd: int, S_max: int, qin_strides, kin_strides, vin_strides, qout_strides, k_strides,
+                   v_strides, qk_norm: bool, eps: float, stream: int) -> None:
+    _check(load().vats_attn_decode_prepare(
+        q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_cache_ptr, v_cache_ptr, seq_lens_ptr, cos_ptr,
+        sin_ptr, B, H, G, hd, S_max, _i64x2(*qin_strides), _i64x2(*kin_strides), _i64x2(*vin_strides),
+        _i64x2(*qout_strides), _i64x3(*k_strides), _i64x3(*v_strides), int(bool(qk_norm)), float(eps), stream))
 
 
 def debug_mask(out_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int], N: int, Tq: int, Tk: int,

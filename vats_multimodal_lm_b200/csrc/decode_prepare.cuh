@@ -1,0 +1,114 @@
+// decode_prepare.cuh — the pre-core step of one cached decode token, fused: qk L2-norm + RoPE + bf16 rounding + KV-cache
+// append (decode part).
+//
+// Reference, per new token at position p (src/optimized_attention.py:463-474):
+//     q, k = F.normalize(q, eps=1e-6), F.normalize(k, eps=1e-6)      utils/attention_utils.py:80-102
+//     q, k = rope(q), rope(k)                                         src/optimized_attention.py:97-143 (interleaved pairs)
+//     cache.update(k, v)                                              src/optimized_attention.py:224-257 (intended contract)
+// Four to six elementwise launches plus the cache write in PyTorch; here one launch: a warp per (sequence, head row),
+// rows = H query heads + G key heads + G value heads.  fp32 arithmetic, one rounding to bf16 at the end.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vats {
+
+struct PrepareParams {
+  const void* q_in;   // [B, H, hd]   (bf16 or fp32)
+  const void* k_in;   // [B, G, hd]
+  const void* v_in;   // [B, G, hd]
+  int in_fp32;
+  __nv_bfloat16* q_out;    // [B, H, hd]
+  __nv_bfloat16* k_cache;  // [B, S_max, G, hd]
+  __nv_bfloat16* v_cache;
+  const int32_t* seq_lens; // [B] length including the new token; position = seq_lens[b] - 1
+  const float* cos_table;  // [positions, hd/2] fp32 or NULL (no RoPE)
+  const float* sin_table;
+  int B, H, G, hd, S_max;
+  long long qi_b, qi_h, ki_b, ki_h, vi_b, vi_h, qo_b, qo_h;
+  long long ks_b, ks_t, ks_h, vs_b, vs_t, vs_h;
+  int qk_norm;
+  float eps;
+};
+
+__device__ __forceinline__ float prepare_load(const void* base, long long idx, int fp32) {
+  return fp32 ? reinterpret_cast<const float*>(base)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+constexpr int kPrepareWarps = 8;
+constexpr int kPrepareMaxPairs = 4;   // per lane: hd <= 256
+
+__global__ void __launch_bounds__(kPrepareWarps * 32) decode_prepare_kernel(const PrepareParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_seq = p.H + 2 * p.G;
+  const long long row = (long long)blockIdx.x * kPrepareWarps + warp;
+  if (row >= (long long)p.B * rows_per_seq) return;
+  const int b = (int)(row / rows_per_seq);
+  const int rr = (int)(row % rows_per_seq);
+  const int L = p.seq_lens[b];
+  if (L <= 0 || L > p.S_max) return;   // nothing to append (or no room: the host validates lengths it can see)
+  const int pos = L - 1;
+
+  // which tensor / head
+  const void* src;
+  long long src_off;
+  __nv_bfloat16* dst;
+  bool rotate;
+  if (rr < p.H) {
+    src = p.q_in; src_off = (long long)b * p.qi_b + (long long)rr * p.qi_h;
+    dst = p.q_out + (long long)b * p.qo_b + (long long)rr * p.qo_h;
+    rotate = true;
+  } else if (rr < p.H + p.G) {
+    const int g = rr - p.H;
+    src = p.k_in; src_off = (long long)b * p.ki_b + (long long)g * p.ki_h;
+    dst = p.k_cache + (long long)b * p.ks_b + (long long)pos * p.ks_t + (long long)g * p.ks_h;
+    rotate = true;
+  } else {
+    const int g = rr - p.H - p.G;
+    src = p.v_in; src_off = (long long)b * p.vi_b + (long long)g * p.vi_h;
+    dst = p.v_cache + (long long)b * p.vs_b + (long long)pos * p.vs_t + (long long)g * p.vs_h;
+    rotate = false;   // values are stored as they are
+  }
+
+  // lane owns element pairs (2i, 2i+1), i = lane, lane + 32, ...
+  const int half = (p.hd + 1) >> 1;
+  float x0[kPrepareMaxPairs], x1[kPrepareMaxPairs];
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < kPrepareMaxPairs; ++u) {
+    const int i = lane + 32 * u;
+    x0[u] = 0.f;
+    x1[u] = 0.f;
+    if (i < half) {
+      x0[u] = prepare_load(src, src_off + 2 * i, p.in_fp32);
+      if (2 * i + 1 < p.hd) x1[u] = prepare_load(src, src_off + 2 * i + 1, p.in_fp32);
+      ss += x0[u] * x0[u] + x1[u] * x1[u];
+    }
+  }
+  float scale = 1.f;
+  if (rotate && p.qk_norm) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    scale = 1.f / fmaxf(sqrtf(ss), p.eps);   // F.normalize: x / max(||x||, eps)
+  }
+  const bool rope = rotate && p.cos_table != nullptr;
+#pragma unroll
+  for (int u = 0; u < kPrepareMaxPairs; ++u) {
+    const int i = lane + 32 * u;
+    if (i < half) {
+      float a = x0[u] * scale, c = x1[u] * scale;
+      if (rope) {
+        const float cs = p.cos_table[(long long)pos * (p.hd >> 1) + i];
+        const float sn = p.sin_table[(long long)pos * (p.hd >> 1) + i];
+        const float ra = a * cs - c * sn;
+        const float rc = a * sn + c * cs;
+        a = ra;
+        c = rc;
+      }
+      dst[2 * i] = __float2bfloat16(a);
+      if (2 * i + 1 < p.hd) dst[2 * i + 1] = __float2bfloat16(c);
+    }
+  }
+}
+
+}  // namespace vats

@@ -146,6 +146,10 @@ class KVCache:
         self.cache[layer_idx]["v"][:, cur:cur + new] = v.to(self.cache[layer_idx]["v"].dtype)
         self._layer_len[layer_idx] = cur + new
 
+    def advance(self, layer_idx: int, new: int) -> None:
+        """Record `new` tokens written into the layer's cache in place (the fused decode step appends on the device)."""
+        self._layer_len[layer_idx] = min(self._layer_len[layer_idx] + new, self.max_seq_len)
+
     def get(self, layer_idx: int, seq_len: int) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         if self.cache is None or seq_len > self._layer_len[layer_idx]:
             return None, None
@@ -212,10 +216,33 @@ class Attention(nn.Module):
         q = q.view(B, T, H, hd)
         k = k.view(B, T, G, hd)
         v = v.view(B, T, G, hd)
+        cached = bool(use_cache) and kv_cache is not None and layer_idx is not None
+
+        # ---- single-token cached decode: qk-norm + RoPE + bf16 rounding + cache append in ONE kernel, then the
+        #      split-K decode kernel (two launches per layer instead of ~10 elementwise ones + the cache write)
+        if cached and T == 1 and padding_mask is None and causal and x.is_cuda and hd % 2 == 0:
+            if kv_cache.cache is None or kv_cache.batch_size != B:
+                kv_cache.initialize(B, device=x.device)
+            past = kv_cache.layer_seq_len(layer_idx)
+            k_all, v_all = kv_cache.cache[layer_idx]["k"], kv_cache.cache[layer_idx]["v"]
+            if k_all.size(2) != G:
+                raise ValueError(f"KVCache stores {k_all.size(2)} heads; the drop-in Attention needs query_groups={G}")
+            if past < kv_cache.max_seq_len and k_all.dtype == torch.bfloat16:
+                left, _ = self._windows(left_window, right_window, causal)
+                cos, sin = self.rope.get_cos_sin_cache(kv_cache.max_seq_len)
+                seq_lens = torch.full((B,), past + 1, dtype=torch.int32, device=x.device)
+                qd, kd, vd = q[:, 0], k[:, 0], v[:, 0]
+                if qd.dtype not in (torch.float32, torch.bfloat16):
+                    qd, kd, vd = qd.float(), kd.float(), vd.float()
+                q_rot = ops.decode_prepare(qd, kd, vd, k_all, v_all, seq_lens, cos, sin, bool(use_qk_norm), 1e-6)
+                kv_cache.advance(layer_idx, 1)
+                o = ops.gqa_swa_decode(q_rot, k_all, v_all, seq_lens, float(self.softmax_scale), left)
+                cache_out = {"k": k_all[:, past:past + 1].to(x.dtype), "v": v_all[:, past:past + 1].to(x.dtype)}
+                return self.w_o(o.to(x.dtype).reshape(B, 1, self.d_model)), cache_out
+
         if use_qk_norm:
             q, k = apply_qk_norm(q, k)
 
-        cached = bool(use_cache) and kv_cache is not None and layer_idx is not None
         past = kv_cache.layer_seq_len(layer_idx) if (cached and kv_cache.cache is not None) else 0
         q = self.rope(q, offset=past)
         k = self.rope(k, offset=past)

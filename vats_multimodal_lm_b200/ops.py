@@ -2,6 +2,7 @@
 
     torch.ops.vats.gqa_swa_prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel) -> o
     torch.ops.vats.gqa_swa_decode(q, k_cache, v_cache, seq_lens, scale, left) -> o
+    torch.ops.vats.decode_prepare(q, k, v, k_cache, v_cache, seq_lens, cos, sin, qk_norm, eps) -> q_rotated  (appends k, v)
     ops.attn_mask(q_valid, k_valid, N, Tq, Tk, causal, left, right)   (plain function) -> uint8 [N,Tq,Tk]
 
 They replace the reference's single library call ``F.scaled_dot_product_attention``
@@ -17,7 +18,7 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -144,6 +145,57 @@ def _(q, k_cache, v_cache, seq_lens, scale, left):
     return q.new_empty(q.shape, dtype=torch.bfloat16)
 
 
+@torch.library.custom_op("vats::decode_prepare", mutates_args=("k_cache", "v_cache"), device_types="cuda")
+def decode_prepare(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                   seq_lens: torch.Tensor, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], qk_norm: bool,
+                   eps: float) -> torch.Tensor:
+    """Fused pre-core step of one cached decode token: qk L2-norm + RoPE at position seq_lens-1 + bf16 rounding + append
+    of k, v to the caches (in place).  q [B,H,hd], k/v [B,G,hd] (bf16 or fp32), caches [B,S_max,G,hd] bf16, seq_lens [B]
+    int32 (length including the new token), cos/sin [positions, hd/2] fp32 or None.  Returns the rotated q (bf16)."""
+    if q.dim() != 3 or k.dim() != 3 or v.shape != k.shape:
+        raise ValueError("q must be [B,H,hd]; k and v must be [B,G,hd] with equal shapes")
+    if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("q, k, v must share one dtype, bf16 or fp32")
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("decode_prepare needs CUDA tensors (no CPU fallback)")
+    _require_cuda_bf16("k_cache", k_cache)
+    _require_cuda_bf16("v_cache", v_cache)
+    B, H, hd = q.shape
+    G = k.size(1)
+    if k_cache.dim() != 4 or v_cache.shape != k_cache.shape or k_cache.size(0) != B or k_cache.size(2) != G or \
+            k_cache.size(3) != hd or k.size(0) != B or k.size(2) != hd:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} cache {tuple(k_cache.shape)}")
+    if k_cache.stride(-1) != 1 or v_cache.stride(-1) != 1:
+        raise ValueError("KV cache must have a contiguous head_dim axis")
+    if seq_lens.shape != (B,) or seq_lens.dtype != torch.int32 or seq_lens.device != q.device:
+        raise ValueError("seq_lens must be an int32 tensor of shape [B] on the same device")
+    if (cos is None) != (sin is None):
+        raise ValueError("cos and sin must both be given or both be None")
+    if cos is not None:
+        if cos.dtype != torch.float32 or sin.dtype != torch.float32 or cos.shape != sin.shape or cos.dim() != 2 or \
+                cos.size(1) != hd // 2 or hd % 2 != 0 or cos.size(0) < k_cache.size(1):
+            raise ValueError("cos / sin must be fp32 [>= S_max, hd/2] tables")
+        cos, sin = cos.contiguous(), sin.contiguous()
+    q, k, v = _rowmajor_last(q), _rowmajor_last(k), _rowmajor_last(v)
+    seq_lens = seq_lens.contiguous()
+    q_out = torch.empty((B, H, hd), dtype=torch.bfloat16, device=q.device)
+    if q_out.numel() == 0:
+        return q_out
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.decode_prepare(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.dtype == torch.float32, q_out.data_ptr(),
+                            k_cache.data_ptr(), v_cache.data_ptr(), seq_lens.data_ptr(),
+                            cos.data_ptr() if cos is not None else None, sin.data_ptr() if sin is not None else None,
+                            B, H, G, hd, k_cache.size(1), q.stride()[:2], k.stride()[:2], v.stride()[:2],
+                            q_out.stride()[:2], k_cache.stride()[:3], v_cache.stride()[:3], qk_norm, eps, stream)
+    return q_out
+
+
+@decode_prepare.register_fake
+def _(q, k, v, k_cache, v_cache, seq_lens, cos, sin, qk_norm, eps):
+    return q.new_empty(q.shape, dtype=torch.bfloat16)
+
+
 def attn_mask(q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], N: int, Tq: int, Tk: int,
               causal: bool, left: int, right: int, device: Optional[torch.device] = None) -> torch.Tensor:
     """The kernels' own mask predicate, materialised (uint8 [N,Tq,Tk]); used for the bit-exact mask tests."""
@@ -175,3 +227,4 @@ def _no_cpu(name):
 
 gqa_swa_prefill.register_kernel("cpu")(_no_cpu("gqa_swa_prefill"))
 gqa_swa_decode.register_kernel("cpu")(_no_cpu("gqa_swa_decode"))
+decode_prepare.register_kernel("cpu")(_no_cpu("decode_prepare"))
