@@ -209,7 +209,7 @@ def run_reference(args):
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -296,6 +296,7 @@ def bench_decode(args, world, peaks):
     # the same step captured once in a CUDA graph (pinned H2D copies, the two kernels, the D2H copy) and replayed:
     # one launch per step instead of six plus the Python op overhead
     e2e_graph = None
+    graph = None
     try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -322,6 +323,11 @@ def bench_decode(args, world, peaks):
             torch.cuda.synchronize()
         if not torch.equal(ref_o, oh):
             raise RuntimeError("graph replay does not reproduce the eager step")
+    except Exception as e:   # the eager number stands
+        graph = None
+        sys.stderr.write(f"bench: CUDA-graph e2e skipped ({type(e).__name__}: {e})\n")
+    # every rank must take the same branch (the timed loop contains barriers)
+    if max_over_ranks(0.0 if graph is not None else 1.0, world) == 0.0:
         barrier_sync(world)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -330,8 +336,6 @@ def bench_decode(args, world, peaks):
         t1 = time.perf_counter()
         barrier_sync(world)
         e2e_graph = world * nbytes / (max_over_ranks(t1 - t0, world) / args.steps) / 1e9
-    except Exception as e:   # the eager number stands
-        sys.stderr.write(f"bench: CUDA-graph e2e skipped ({type(e).__name__}: {e})\n")
     clocks = sampler.stop()   # sampled over the device-timed region and the end-to-end region (both under load)
     e2e_value = e2e_graph if e2e_graph is not None else e2e_eager
     h2d = qh.numel() * 2 + knh.numel() * 2 + vnh.numel() * 2 + lens_h.numel() * 4
@@ -426,8 +430,12 @@ def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool, layout:
         res["ms_compute_plus_allgather_overlapped"] = max_over_ranks((t1 - t0) / steps * 1e3, world)
         del full
         # ... and with copy-engine peer writes into symmetric memory instead of NCCL (needs no SM: really overlaps)
+        pg, err = None, None
         try:
             pg = sharding.PeerGather(N, T, H, hd, torch.bfloat16, dev)
+        except Exception as e:
+            err = f"{type(e).__name__}: {e}"
+        if max_over_ranks(0.0 if pg is not None else 1.0, world) == 0.0:   # every rank takes the same branch
             for _ in range(2):
                 full = sharding.local_attention_gather(core, q, k, v, N, H, G, chunks=4, causal=c["causal"], peer=pg)
             barrier_sync(world)
@@ -437,9 +445,10 @@ def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool, layout:
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             res["ms_compute_plus_peer_gather_overlapped"] = max_over_ranks((t1 - t0) / steps * 1e3, world)
-            del full, pg
-        except Exception as e:
-            res["peer_gather_error"] = f"{type(e).__name__}: {e}"
+            del full
+        else:
+            res["peer_gather_error"] = err or "symmetric memory unavailable on another rank"
+        del pg
     units = world if (not shard) else 1  # unsharded workloads are replicated per rank (weak)
     fl = prefill_flops(c) * units
     by = prefill_bytes(c) * units
@@ -527,10 +536,19 @@ def run_ours(args):
             "device_ms_per_step": r["dev_ms"],
             "cpu_baseline": cpu, "other_workloads": other, "peaks": peaks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -543,6 +561,12 @@ def main():
     ap.add_argument("--cache-layout", default="bshd", choices=["bshd", "bhsd"],
                     help="storage order of the KV cache behind its [B,S,G,hd] shape")
     args = ap.parse_args()
+    # Exactly one line on stdout: libraries write banners there (NCCL prints its version at the first communicator),
+    # so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
