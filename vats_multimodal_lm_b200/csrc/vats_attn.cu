@@ -22,6 +22,7 @@
 #include "prefill_tc.cuh"
 #include "prefill_short.cuh"
 #include "decode_prepare.cuh"
+#include "repack.cuh"
 
 namespace {
 
@@ -328,6 +329,90 @@ int launch_short(const PrefillArgs& A, cudaStream_t st) {
   return VATS_OK;
 }
 
+int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st);
+
+// q / k / v with rows TMA cannot address: one streaming repack into a stream-ordered scratch buffer (head stride
+// rounded up to 8 elements), then the TMA-fed kernel on the copies.  Returns -1 if the scratch cannot be had
+// (the caller then uses the kernel's own cp.async staging variant).
+int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VATS_PREFILL_REPACK");  // tuning knob: 0 = stage inside the kernel instead
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled) return -1;
+  const int hd_pad = (A.hd + 7) / 8 * 8;
+  const void* src[3] = {A.q, A.k, A.v};
+  const int64_t* str[3] = {A.qs, A.ks, A.vs};
+  const int Ts[3] = {A.Tq, A.Tk, A.Tk};
+  const int heads[3] = {A.H, A.G, A.G};
+  const LoadMode modes[3] = {pl.q, pl.k, pl.v};
+  size_t off[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 3; ++i) {
+    const size_t bytes = modes[i] == LoadMode::kLdg ? (size_t)A.N * Ts[i] * heads[i] * hd_pad * 2 : 0;
+    off[i + 1] = off[i] + ((bytes + 255) & ~(size_t)255);
+  }
+  {
+    // keep freed scratch in the device's stream-ordered pool (the default threshold hands it back to the driver at
+    // every synchronisation, which makes each call pay for a fresh multi-hundred-MB allocation)
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != pool_dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      (void)cudaGetLastError();
+      pool_dev = dev;
+    }
+  }
+  void* ws = nullptr;
+  if (cudaMallocAsync(&ws, off[3], st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  vats::RepackParams R;
+  std::memset(&R, 0, sizeof(R));
+  R.hd2 = A.hd / 2;
+  R.hd_pad = hd_pad;
+  int64_t new_str[3][3];
+  PrefillArgs B = A;
+  long long max_rows = 0;
+  int nrep = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (modes[i] != LoadMode::kLdg) continue;
+    vats::RepackTensor& t = R.t[nrep++];
+    t.src = reinterpret_cast<const __nv_bfloat16*>(src[i]);
+    t.dst = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + off[i]);
+    t.s_n = str[i][0]; t.s_t = str[i][1]; t.s_h = str[i][2];
+    t.T = Ts[i]; t.heads = heads[i];
+    t.rows = (long long)A.N * Ts[i] * heads[i];
+    if (t.rows > max_rows) max_rows = t.rows;
+    new_str[i][2] = hd_pad;
+    new_str[i][1] = (int64_t)heads[i] * hd_pad;
+    new_str[i][0] = (int64_t)Ts[i] * heads[i] * hd_pad;
+    if (i == 0) { B.q = t.dst; B.qs = new_str[0]; }
+    if (i == 1) { B.k = t.dst; B.ks = new_str[1]; }
+    if (i == 2) { B.v = t.dst; B.vs = new_str[2]; }
+  }
+  long long blocks = (max_rows + vats::kRepackWarps * vats::kRepackRows - 1) / (vats::kRepackWarps * vats::kRepackRows);
+  const long long cap = (long long)sm_count() * 64;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  vats::repack_kernel<<<dim3((unsigned)blocks, (unsigned)nrep), vats::kRepackWarps * 32, 0, st>>>(R);
+  int rc = VATS_OK;
+  if (cudaGetLastError() != cudaSuccess) {
+    rc = fail(VATS_ERR_CUDA, "repack kernel launch failed");
+  } else {
+    TcPlan pl2{LoadMode::kTma, LoadMode::kTma, LoadMode::kTma};
+    rc = launch_tc(B, pl2, st);
+  }
+  cudaFreeAsync(ws, st);
+  if (rc == VATS_OK) g_launches += 1;
+  return rc;
+}
+
 int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   vats::TcParams P;
   std::memset(&P, 0, sizeof(P));
@@ -338,6 +423,10 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.pairs = (P.a.hpg + 1) / 2;
   // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  if (any_ldg) {
+    const int rc2 = launch_tc_repacked(A, pl, st);
+    if (rc2 >= 0) return rc2;
+  }
   {
     auto al8 = [&](const void* ptr, const int64_t* st3) {
       return (reinterpret_cast<uintptr_t>(ptr) & 7u) == 0 && st3[0] % 4 == 0 && st3[1] % 4 == 0 && st3[2] % 4 == 0;
