@@ -163,3 +163,58 @@ def test_vit_reference_smoke_shapes():
     pm = torch.randint(0, 2, (4, 5 * 16), dtype=torch.bool, device=dev)
     y3 = b3(x=x3, grid_size=(5, 4, 4), use_mqa=False, use_qk_norm=True, window_size=(-1, -1), padding_mask=pm)
     assert y3.shape == x3.shape and torch.isfinite(y3).all()
+
+
+def test_vit3d_reference_attention_tests_rerun_on_dropin():
+    """reference tests/transformers/vision/vit_3d/attention_tests.py on the drop-in (xsmall config: d_model 240,
+    4 heads / 2 groups -> hd 60, patch (2,8,8)): output shapes with / without padding mask and window, qk-norm on / off,
+    zero input frames, batch sizes 1..16, 1..25 input frames (grid depth 1..13), grid resolutions 1x1..16x16 — every
+    output finite.  The inputs are built directly at the grid the reference's PatchEmbeddings3D would produce."""
+    torch.manual_seed(42)
+    dev = "cuda"
+    d, H, G = 240, 4, 2
+    attn = vl.SpatioTemporalAttention(d, H, G, 30000.0, (2, 8, 8)).to(dev)
+    assert attn.w_qkv.weight.shape == (d + 2 * G * (d // H), d) and attn.w_o.weight.shape == (d, d)
+
+    def run(B, gT, gH, gW, window=(-1, -1), pad=True, qk_norm=True):
+        x = torch.randn(B, gT, gH * gW, d, device=dev)
+        pm = None
+        if pad:
+            pm = torch.rand(B, gT * gH * gW, device=dev) > 0.2
+            if pm.numel():
+                pm[:, 0] = True
+        out = attn(x, (gT, gH, gW), False, qk_norm, window, pm)
+        assert out.shape == (B, gT, gH * gW, d)
+        assert torch.isfinite(out).all()
+        return out
+
+    run(2, 4, 2, 2)                                  # test_output_shape / test_padding (T=8 frames, 16x16 input)
+    run(2, 4, 2, 2, pad=False)                       # test_no_padding
+    run(2, 4, 2, 2, qk_norm=False)                   # test_no_qk_norm_stability
+    run(2, 4, 16, 16, window=(256, 256))             # test_windowed_attn at the target-size grid
+    run(2, 0, 2, 2)                                  # test_zero_input_frames
+    for b in (1, 2, 4, 8, 16):                       # test_variable_batch_sizes
+        run(b, 4, 2, 2)
+    for g in (1, 2, 4, 16):                          # test_variable_resolutions
+        run(2, 4, g, g)
+    for frames in range(1, 26):                      # test_variable_input_frames
+        run(2, (frames + 1) // 2, 2, 2)
+
+
+def test_vit2d_reference_attention_tests_rerun_on_dropin():
+    """reference tests/transformers/vision/vit_2d/attention_tests.py on the drop-in: shapes, fused projection weights,
+    windowed / unwindowed, qk-norm on / off, batch sizes 1..64, all finite."""
+    torch.manual_seed(42)
+    dev = "cuda"
+    d, H, G, target, patch = 384, 8, 4, 96, 16
+    hd = d // H
+    T = (target // patch) ** 2
+    attn = vl.SpatialAttention(d, H, G, 10000.0, target, patch, hd ** -0.5, True, False, True).to(dev).eval()
+    assert attn.qkv_proj.weight.shape == (d + 2 * G * hd, d) and attn.o_proj.weight.shape == (d, d)
+    x = torch.randn(2, T, d, device=dev)
+    for (qk_norm, left, right) in [(True, -1, -1), (False, -1, -1), (True, 4, 4), (True, 0, 0)]:
+        y = attn(x, False, qk_norm, left, right)
+        assert y.shape == x.shape and torch.isfinite(y).all()
+    for b in (1, 2, 4, 8, 16, 32, 64):
+        y = attn(torch.randn(b, T, d, device=dev), False, True, -1, -1)
+        assert y.shape == (b, T, d) and torch.isfinite(y).all()

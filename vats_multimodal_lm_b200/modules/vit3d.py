@@ -135,6 +135,8 @@ class SpatioTemporalAttention(nn.Module):
         if window_size is not None and mode != "reference_sdpa":
             window = (int(window_size[0]), int(window_size[1]))
         B = x.size(0)
+        if x.numel() == 0:   # no frames / no patches: nothing to attend (the reference's `.view(..., -1, ...)` is ambiguous here)
+            return x.new_zeros(B, x.size(1), x.size(2), self.d_model)
         spatial = self._pass(x, use_mqa, use_qk_norm, grid_size, window, padding_mask, "spatial")
         spatial = spatial.view(B, grid_size[0], -1, self.d_model)
         temporal = self._pass(spatial, use_mqa, use_qk_norm, grid_size, window, padding_mask, "temporal")
