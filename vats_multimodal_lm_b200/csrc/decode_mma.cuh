@@ -91,7 +91,7 @@ __device__ __forceinline__ DmItem dm_decode_item(const DecodeMmaParams& P, int i
 
 // HD: head dim (multiple of 16, <= 128).  Shared memory: [stages][K halves | V halves][32 keys][128 B] + merge scratch.
 template <int HD, int NCW, int SK>
-__global__ void __launch_bounds__(2 * NCW * 32, 1)
+__global__ void __launch_bounds__((2 * NCW + 1) * 32, 1)
 decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap tmap_k,
                   const __grid_constant__ CUtensorMap tmap_v) {
   using namespace ptx;
@@ -115,7 +115,8 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
   float* scr_ml = scr + kDmConsumerWarps * kDmMaxHeads * SCR_ROW;                 // [4][8][2]
   uint64_t* full = reinterpret_cast<uint64_t*>(scr_ml + kDmConsumerWarps * kDmMaxHeads * 2);
   uint64_t* empty = full + P.stages;
-  int* s_flag = reinterpret_cast<int*>(empty + P.stages);
+  uint64_t* scr_full = empty + P.stages;          // [NCW] consumer w has put its (m, l, O) of an item into its scratch rows
+  uint64_t* scr_empty = scr_full + kDmConsumerWarps;   // [NCW] ... and the flush warp has read them
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -124,9 +125,134 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
       mbar_init(smem_u32(&full[s]), 1);
       mbar_init(smem_u32(&empty[s]), 1);
     }
+    for (int w = 0; w < kDmConsumerWarps; ++w) {
+      mbar_init(smem_u32(&scr_full[w]), 1);
+      mbar_init(smem_u32(&scr_empty[w]), 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
+
+  if (warp == 2 * kDmConsumerWarps) {
+    // =================================================================== flush warp: the end of every item, off the
+    // consumers' critical path.  It merges the NCW warps' (m, l, O) from the scratch rows, writes the bf16 output
+    // (one split) or the item's partial to the workspace, and — splits only — signals the unit's counter; the last
+    // split to arrive merges them.  The gpu-scope fences and the atomic round trip (micro-seconds) used to stall
+    // all consumer warps behind CTA barriers at every item end: 31 us of a 191 us launch.
+    uint32_t fph = 0u;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      const DmItem it = dm_decode_item<SK>(P, item);
+      const int h0 = it.g * d.hpg + it.hb * P.hpg_tile;
+      const int nh = min(P.hpg_tile, d.hpg - it.hb * P.hpg_tile);
+      const int unit = (it.b * d.G + it.g) * d.head_batches + it.hb;
+      for (int w = 0; w < kDmConsumerWarps; ++w) mbar_wait(smem_u32(&scr_full[w]), fph);
+      fph ^= 1u;
+      // lane owns output columns lane, lane + 32, ...; the head loop is unrolled so every load is in flight at once
+      constexpr int CPL = (HD + 31) / 32;
+#pragma unroll
+      for (int h = 0; h < kDmMaxHeads; ++h) {
+        if (h < nh) {
+          float M = -INFINITY;
+#pragma unroll
+          for (int w = 0; w < kDmConsumerWarps; ++w) M = fmaxf(M, scr_ml[(w * kDmMaxHeads + h) * 2]);
+          const float Mref = (M == -INFINITY) ? 0.f : M;
+          float acc[CPL], L = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+#pragma unroll
+          for (int w = 0; w < kDmConsumerWarps; ++w) {
+            const float mw = scr_ml[(w * kDmMaxHeads + h) * 2];
+            const float f = (mw == -INFINITY) ? 0.f : ex2(mw - Mref);
+            L += f * scr_ml[(w * kDmMaxHeads + h) * 2 + 1];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+              if (c * 32 + lane < HD) acc[c] += f * scr[(w * kDmMaxHeads + h) * SCR_ROW + c * 32 + lane];
+          }
+          const int hq = h0 + h;
+          if (d.num_splits == 1) {
+            const float invL = L > 0.f ? 1.f / L : 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+              if (c * 32 + lane < HD)
+                d.o[it.b * d.os_b + (long long)hq * d.os_h + c * 32 + lane] = __float2bfloat16(acc[c] * invL);
+          } else {
+            const long long slot = (long long)(it.b * d.H + hq) * d.num_splits + it.split;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+              if (c * 32 + lane < HD) d.ws_acc[slot * HD + c * 32 + lane] = acc[c];
+            if (lane == 0) {
+              d.ws_ml[slot * 2] = M;
+              d.ws_ml[slot * 2 + 1] = L;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        for (int w = 0; w < kDmConsumerWarps; ++w) mbar_arrive(smem_u32(&scr_empty[w]));   // the consumers may refill
+      if (d.num_splits > 1) {
+        // ---- the last split of this unit to arrive merges all of them.  One lane fences: __syncwarp orders the
+        //      other lanes' partial stores before it and the gpu-scope fence is cumulative.
+        int last = 0;
+        if (lane == 0) {
+          __threadfence();
+          const int old = atomicAdd(&P.counters[unit], 1);
+          __threadfence();
+          last = (old == d.num_splits - 1) ? 1 : 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          float accm[kDmMaxHeads][CPL], Mh[kDmMaxHeads], Lh[kDmMaxHeads];
+#pragma unroll
+          for (int h = 0; h < kDmMaxHeads; ++h) {
+            Mh[h] = -INFINITY;
+            Lh[h] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) accm[h][c] = 0.f;
+          }
+          // two passes over the splits, every head's loads of a pass issued together (L2 latency paid once per pass)
+          for (int sp = 0; sp < d.num_splits; ++sp) {
+#pragma unroll
+            for (int h = 0; h < kDmMaxHeads; ++h)
+              if (h < nh) Mh[h] = fmaxf(Mh[h], __ldcg(d.ws_ml + ((long long)(it.b * d.H + h0 + h) * d.num_splits + sp) * 2));
+          }
+          for (int sp = 0; sp < d.num_splits; ++sp) {
+            float2 ml[kDmMaxHeads];
+            float v[kDmMaxHeads][CPL];
+#pragma unroll
+            for (int h = 0; h < kDmMaxHeads; ++h) {
+              ml[h] = make_float2(-INFINITY, 0.f);
+              const long long slot = (long long)(it.b * d.H + h0 + h) * d.num_splits + sp;
+              if (h < nh) ml[h] = __ldcg(reinterpret_cast<const float2*>(d.ws_ml + slot * 2));
+#pragma unroll
+              for (int c = 0; c < CPL; ++c) {
+                v[h][c] = 0.f;
+                if (h < nh && c * 32 + lane < HD) v[h][c] = __ldcg(d.ws_acc + slot * HD + c * 32 + lane);
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < kDmMaxHeads; ++h) {
+              const float Mref = (Mh[h] == -INFINITY) ? 0.f : Mh[h];
+              const float f = (ml[h].x == -INFINITY) ? 0.f : ex2(ml[h].x - Mref);
+              Lh[h] += f * ml[h].y;
+#pragma unroll
+              for (int c = 0; c < CPL; ++c) accm[h][c] += f * v[h][c];
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < kDmMaxHeads; ++h) {
+            const float invL = Lh[h] > 0.f ? 1.f / Lh[h] : 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+              if (h < nh && c * 32 + lane < HD)
+                d.o[it.b * d.os_b + (long long)(h0 + h) * d.os_h + c * 32 + lane] = __float2bfloat16(accm[h][c] * invL);
+          }
+          if (lane == 0) P.counters[unit] = 0;  // leave the workspace ready for the next call
+        }
+      }
+    }
+    return;
+  }
 
   if (warp >= kDmConsumerWarps) {
     // =================================================================== producers: warp NCW + p feeds consumer p.
@@ -168,6 +294,7 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
   int slot = warp;      // ring slot of this warp's next stage
   uint32_t cph = 0u;    // its phase parity
   int gs_mod = 0;       // (global stage index of the item's first stage) mod NCW
+  uint32_t sph = 0u;    // phase parity of this warp's scratch hand-off
 
   for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
     const DmItem it = dm_decode_item<SK>(P, item);
@@ -320,9 +447,11 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
     }
     gs_mod = (gs_mod + it.nst) & (kDmConsumerWarps - 1);
 
-    // ---- merge the four warps' (m, l, O) for this item through shared memory
+    // ---- hand this warp's (m, l, O) of the item to the flush warp through its scratch rows and move on: no CTA-wide
+    //      barrier, no global fence on this path
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    mbar_wait(smem_u32(&scr_empty[warp]), sph ^ 1u);   // the previous item's rows have been read
     if (quad < kDmMaxHeads) {
       float* row = scr + (warp * kDmMaxHeads + quad) * SCR_ROW;
 #pragma unroll
@@ -335,68 +464,9 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
         scr_ml[(warp * kDmMaxHeads + quad) * 2 + 1] = l_run;
       }
     }
-    consumer_barrier<kDmConsumerWarps * 32>();
-    const int tid = threadIdx.x;  // consumer thread index
-    const int unit = (it.b * d.G + it.g) * d.head_batches + it.hb;
-    for (int idx = tid; idx < nh * HD; idx += kDmConsumerWarps * 32) {
-      const int h = idx / HD, e = idx % HD;
-      float M = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < kDmConsumerWarps; ++w) M = fmaxf(M, scr_ml[(w * kDmMaxHeads + h) * 2]);
-      const float Mref = (M == -INFINITY) ? 0.f : M;
-      float acc = 0.f, L = 0.f;
-#pragma unroll
-      for (int w = 0; w < kDmConsumerWarps; ++w) {
-        const float mw = scr_ml[(w * kDmMaxHeads + h) * 2];
-        const float f = (mw == -INFINITY) ? 0.f : ex2(mw - Mref);
-        acc += f * scr[(w * kDmMaxHeads + h) * SCR_ROW + e];
-        L += f * scr_ml[(w * kDmMaxHeads + h) * 2 + 1];
-      }
-      const int hq = h0 + h;
-      if (d.num_splits == 1) {
-        d.o[it.b * d.os_b + (long long)hq * d.os_h + e] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
-      } else {
-        const long long slot = (long long)(it.b * d.H + hq) * d.num_splits + it.split;
-        d.ws_acc[slot * HD + e] = acc;
-        if (e == 0) {
-          d.ws_ml[slot * 2] = M;
-          d.ws_ml[slot * 2 + 1] = L;
-        }
-      }
-    }
-    if (d.num_splits > 1) {
-      // ---- the last CTA to deliver a split of this unit merges all of them.  One thread fences: the barrier makes
-      //      the other threads' partial stores visible to it and the gpu-scope fence is cumulative.
-      consumer_barrier<kDmConsumerWarps * 32>();
-      if (tid == 0) {
-        __threadfence();
-        const int old = atomicAdd(&P.counters[unit], 1);
-        __threadfence();
-        *s_flag = (old == d.num_splits - 1) ? 1 : 0;
-      }
-      consumer_barrier<kDmConsumerWarps * 32>();
-      if (*s_flag) {
-        for (int idx = tid; idx < nh * HD; idx += kDmConsumerWarps * 32) {
-          const int h = idx / HD, e = idx % HD;
-          const int hq = h0 + h;
-          const long long slot0 = (long long)(it.b * d.H + hq) * d.num_splits;
-          const float* ml = d.ws_ml + slot0 * 2;
-          float M = -INFINITY;
-          for (int sp = 0; sp < d.num_splits; ++sp) M = fmaxf(M, __ldcg(ml + 2 * sp));
-          const float Mref = (M == -INFINITY) ? 0.f : M;
-          float acc = 0.f, L = 0.f;
-          for (int sp = 0; sp < d.num_splits; ++sp) {
-            const float mw = __ldcg(ml + 2 * sp);
-            const float f = (mw == -INFINITY) ? 0.f : ex2(mw - Mref);
-            acc += f * __ldcg(d.ws_acc + (slot0 + sp) * HD + e);
-            L += f * __ldcg(ml + 2 * sp + 1);
-          }
-          d.o[it.b * d.os_b + (long long)hq * d.os_h + e] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
-        }
-        if (tid == 0) P.counters[unit] = 0;  // leave the workspace ready for the next call
-      }
-    }
-    consumer_barrier<kDmConsumerWarps * 32>();  // scratch is reused by the next item
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&scr_full[warp]));
+    sph ^= 1u;
   }
 }
 
@@ -407,7 +477,7 @@ __host__ inline size_t decode_mma_smem_bytes(int stages) {
   constexpr int STAGE_BYTES = 2 * HALVES * SK * 128;
   constexpr int SCR_ROW = HD + 4;
   return 1024 + (size_t)stages * STAGE_BYTES + (size_t)kDmConsumerWarps * kDmMaxHeads * (SCR_ROW + 2) * sizeof(float) +
-         (size_t)stages * 16 + 64;
+         (size_t)stages * 16 + (size_t)2 * kDmConsumerWarps * 8 + 64;
 }
 
 }  // namespace vats

@@ -646,7 +646,7 @@ int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUt
   }
   int grid = sm_count();
   if (grid > P.num_items) grid = P.num_items;
-  vats::decode_mma_kernel<HD, NCW, SK><<<grid, 2 * NCW * 32, smem, st>>>(P, mk, mv);
+  vats::decode_mma_kernel<HD, NCW, SK><<<grid, (2 * NCW + 1) * 32, smem, st>>>(P, mk, mv);
   CUDA_TRY(cudaGetLastError());
   return VATS_OK;
 }
