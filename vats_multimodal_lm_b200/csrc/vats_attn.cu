@@ -624,12 +624,15 @@ size_t decode_mma_ws_bytes(int B, int H, int G, int hd, int S_max, int left) {
 
 template <int HD, int NCW, int SK>
 int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
-  // ring depth: as deep as the 227 KB of shared memory allow (bytes in flight are what hides the HBM latency)
-  int stages = 48;
-  while (vats::decode_mma_smem_bytes<HD, NCW, SK>(stages) > 227 * 1024 && stages > 2) --stages;
+  // ring depth: two stages per consumer warp (8 x 16 KB = 128 KB in flight per SM).  Measured on cfg2 with the flush
+  // warp in place: 4 stages 0.195 ms, 8 stages 0.165 ms, 12 stages (all 227 KB) 0.174 ms — more bytes in flight than
+  // the latency-bandwidth product needs only add DRAM page conflicts.
+  int max_stages = 48;
+  while (vats::decode_mma_smem_bytes<HD, NCW, SK>(max_stages) > 227 * 1024 && max_stages > 2) --max_stages;
+  int stages = 2 * NCW < max_stages ? 2 * NCW : max_stages;
   if (const char* e = getenv("VATS_DECODE_STAGES")) {  // tuning / debugging knob
     const int want = atoi(e);
-    if (want >= 2 && want < stages) stages = want;
+    if (want >= 2 && want <= max_stages) stages = want;
   }
   // The ring depth MUST be a multiple of the consumer-warp count, so that a slot is always consumed by the same
   // warp: a consumer waits on a slot's "full" barrier by phase parity, which is only sound if it has itself seen
