@@ -3,8 +3,8 @@
 // Same contract as decode.cuh (reference src/optimized_attention.py:508-516 + 709-714, cache KVCache :169-287); this
 // is the fast path for TMA-addressable caches (head_dim % 16 == 0, 16-byte aligned strides).
 //
-// The kernel is a byte pump: decode is 4 flop/byte, so everything is organised around keeping >= 128 KB of K/V in
-// flight per SM and spending almost no issue slots per byte.
+// The kernel is a byte pump: decode is 4 flop/byte, so everything is organised around keeping 128 KB of K/V in
+// flight per SM, spending almost no issue slots per byte, and never stalling the consumers at an item boundary.
 //   * persistent CTAs (one per SM) walk a static list of work items (sequence b, KV group g, head batch, split);
 //   * warps NCW..2NCW-1 are producers (one elected lane each, producer p feeds consumer p): per stage of SK keys
 //     they issue the TMA boxes of K and V (128B-swizzled) into an mbarrier ring that runs across item boundaries —
@@ -18,8 +18,10 @@
 //     swizzled tiles with ldmatrix / ldmatrix.trans, conflict-free.  That is ~300 instructions per 16 KB of cache
 //     instead of ~2000 on the FP32 pipe; the tensor pipe is <5 % busy, which is the point: the SM only moves bytes.
 //   * online softmax per stage in registers, quad shuffles for the row max / sum;
-//   * at the end of an item the consumer warps merge (m, l, O) through shared memory; split partials go to the fp32
-//     workspace and the LAST CTA to finish a (b, g, head batch) merges its splits and writes bf16 — no second launch.
+//   * at the end of an item a consumer warp leaves its (m, l, O) in its scratch rows (mbarrier hand-off) and goes on;
+//     warp 2*NCW, the flush warp, merges the warps' rows, writes bf16 (one split) or the fp32 partial to the workspace,
+//     and the LAST split to reach a (b, g, head batch) unit's counter merges the splits — no second launch, and no
+//     CTA barrier, global fence or atomic on the consumers' path.
 #pragma once
 #include "decode.cuh"
 #include "ptx.cuh"

@@ -13,9 +13,10 @@
 //   warps 0-3   softmax warpgroup of tile 0: thread r owns S row r (TMEM lane r) — row max / row sum are in-thread
 //   warps 4-7   softmax warpgroup of tile 1
 //   warps 8-10  TMA producers (one lane each): K ring, V ring, Q tiles — mbarrier-guarded, 128B-swizzled boxes
-//   warps 8-10  (only for head dims TMA cannot address, e.g. 60 or 66: rows are 4-byte, not 16-byte, aligned)
-//               LDG staging loaders: coalesced 32-bit loads, stored into the same 128B-swizzled layout
-//   warp  11    MMA issuer (one elected lane): S = Q·K^T (SS, both K-major), O += P·V (TS: P from TMEM, V MN-major)
+//   warps 8-10  (kLdg instantiation: head dims TMA cannot address, e.g. 60 or 66 — rows 4- or 8-byte aligned)
+//               staging loaders: cp.async copies into the same 128B-swizzled layout, two tiles in flight per thread
+//   warp  11    MMA warp (all lanes convergent, one elected): S = Q·K^T (SS, both K-major), O += P·V (TS: P from
+//               TMEM, V MN-major)
 //   Registers are re-balanced with setmaxnreg: 80 for warps 8-11, 208 for the softmax warps.
 //
 //   TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (bf16) aliases the first 64 columns of S.
