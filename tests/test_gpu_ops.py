@@ -371,3 +371,23 @@ def test_decode_prepare_matches_oracle_and_feeds_decode(B, H, G, hd, S, dtype):
     q2 = ops.decode_prepare(q.cuda(), k.cuda(), v.cuda(), dk2, dv2, lens.cuda(), None, None, False, 1e-6)
     q2_ref, k2_ref, _ = decode_prepare_explicit(q, k, v, kc, vc, lens, None, None, False)
     assert torch.equal(q2.cpu()[live], q2_ref.bfloat16()[live]) and torch.equal(dk2.cpu(), k2_ref.bfloat16())
+
+
+def test_decode_random_geometries_back_to_back():
+    """Many decode calls of different geometry on one stream: workspace reuse across shapes and split counts, empty
+    sequences, every TMA head dim — exercises the consumer / flush-warp hand-off across item boundaries."""
+    g = torch.Generator().manual_seed(123)
+    for it in range(24):
+        B = int(torch.randint(1, 70, (1,), generator=g))
+        G = int(torch.randint(1, 5, (1,), generator=g))
+        H = G * int(torch.randint(1, 9, (1,), generator=g))
+        hd = [16, 32, 64, 128][it % 4]
+        S = int(torch.randint(1, 2500, (1,), generator=g))
+        left = [-1, 0, 17, 300, 4096][it % 5]
+        kc = torch.nn.functional.normalize(torch.randn(B, S, G, hd, generator=g), dim=-1).bfloat16()
+        vc = torch.randn(B, S, G, hd, generator=g).bfloat16()
+        q = torch.nn.functional.normalize(torch.randn(B, H, hd, generator=g), dim=-1).bfloat16()
+        lens = torch.randint(0, S + 1, (B,), generator=g).int()
+        o = ops.gqa_swa_decode(q.cuda(), kc.cuda(), vc.cuda(), lens.cuda(), hd ** -0.5, left)
+        ref = decode_explicit(q, kc, vc, lens, hd ** -0.5, left)
+        check_close(o, ref, f"decode {(B, H, G, hd, S, left)}")
