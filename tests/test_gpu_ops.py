@@ -391,3 +391,19 @@ def test_decode_random_geometries_back_to_back():
         o = ops.gqa_swa_decode(q.cuda(), kc.cuda(), vc.cuda(), lens.cuda(), hd ** -0.5, left)
         ref = decode_explicit(q, kc, vc, lens, hd ** -0.5, left)
         check_close(o, ref, f"decode {(B, H, G, hd, S, left)}")
+
+
+@pytest.mark.parametrize("N,Tq,Tk", [(3, 1, 300), (5, 4, 700), (2, 15, 129), (4, 2, 64)])
+def test_few_query_tokens_against_many_keys(N, Tq, Tk):
+    """Chunked-prefill tails / speculative-token verification: Tq << Tk, bottom-right aligned causal window.  AUTO picks
+    the tensor-core kernel (Tk >= 32) and both kernels agree with the oracle."""
+    H, G, hd = 8, 2, 64
+    q, k, v = make_qkv(N, Tq, Tk, H, G, hd, seed=81)
+    ref = oracle_prefill(q, k, v, hd ** -0.5, True, 100, 0)
+    for kern in (AUTO, TC, SIMT):
+        o = run_prefill(q, k, v, hd ** -0.5, True, 100, 0, kernel=kern)
+        check_close(o, ref, f"few-query {(N, Tq, Tk)} kernel {kern}")
+    s = lambda t: tuple(t.stride()[:3])
+    dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
+    assert _ffi.prefill_plan(N, Tq, Tk, H, G, hd, s(dq), s(dk), s(dv), s(dq), dq.data_ptr(), dk.data_ptr(),
+                             dv.data_ptr()) == TC
