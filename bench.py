@@ -361,7 +361,7 @@ def bench_decode(args, world, peaks):
                       frac=achieved / peaks["hbm_gbs"], traffic=traffic,
                       peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})",
                       frac_of_8tbs_spec=achieved / 8000.0,
-                      kernel="decode_split_kernel (+ decode_combine_kernel, timed together)",
+                      kernel="decode_mma_kernel<128,4,32> (one launch per step: TMA ring + mma.sync consumers + flush warp)",
                       algorithmic_bytes_per_launch=nbytes,
                       launch_ms_mean=dev_ms, launch_ms_min=min(per_launch_ms)),
     )
