@@ -114,6 +114,22 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
 size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left);
 
 /*
+ * Pre-core producers of a prefill chunk, fused into one launch (prefill half, 1-D RoPE):
+ * q, k [N,T,heads,hd] are L2-normalised (utils/attention_utils.py:80-102, if qk_norm) and rotated at position
+ * pos0 + t (src/optimized_attention.py:97-143, order :467-474); v is passed through; all three are rounded to bf16
+ * once and written with the caller's output strides — typically a head stride rounded up to 8 elements, the layout
+ * the tensor-core kernel can fetch with TMA (this replaces the normalise / rotate / cast / pad passes of the PyTorch
+ * path).  in_dtype: 0 = bf16, 1 = fp32.  Strides are (sequence, token, head) in elements.
+ */
+int vats_attn_prefill_prepare(const void* q_in, const void* k_in, const void* v_in, int in_dtype,
+                              void* q_out, void* k_out, void* v_out,
+                              const float* cos_table, const float* sin_table,
+                              int N, int T, int H, int G, int hd, int pos0,
+                              const int64_t qin_strides[3], const int64_t kin_strides[3], const int64_t vin_strides[3],
+                              const int64_t qout_strides[3], const int64_t kout_strides[3], const int64_t vout_strides[3],
+                              int qk_norm, float eps, void* stream);
+
+/*
  * Pre-core step of one cached decode token, fused into one launch (decode part):
  *     q, k = F.normalize(q, eps), F.normalize(k, eps)     utils/attention_utils.py:80-102   (only if qk_norm != 0)
  *     q, k = rope(q), rope(k)  at position seq_lens[b]-1  src/optimized_attention.py:97-143 (interleaved pairs 2i, 2i+1;

@@ -113,8 +113,25 @@ def prepare_case(name, seed, H, G, hd, theta, P, B, use_qk_norm=True):
     print(name, tuple(qr[:, P].shape))
 
 
+def prepare_seq_case(name, seed, H, G, hd, theta, T, B, use_qk_norm=True):
+    """The same producers over a whole sequence (positions 0 .. T-1), as the reference's prefill runs them."""
+    m = ref.llm()
+    from utils.attention_utils import apply_qk_norm
+    torch.manual_seed(seed)
+    rope = m.RoPE(hd, theta)
+    q = torch.randn(B, T, H, hd)
+    k = torch.randn(B, T, G, hd)
+    with torch.no_grad():
+        qn, kn = apply_qk_norm(q, k) if use_qk_norm else (q, k)
+        qr, kr = rope(qn), rope(kn)
+    torch.save({"kind": "prepare_seq", "H": H, "G": G, "hd": hd, "theta": theta, "T": T, "use_qk_norm": use_qk_norm,
+                "q_in": q, "k_in": k, "q_out": qr, "k_out": kr}, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(qr.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    prepare_seq_case("prepareseq_hd60_t40", 403, 6, 2, 60, 10000.0, 40, 2)
     # pre-core step of a decode token (qk-norm + RoPE at position P)
     prepare_case("prepare_hd128_p300", 401, 8, 2, 128, 10000.0, 300, 3)
     prepare_case("prepare_hd60_p17_nonorm", 402, 6, 2, 60, 10000.0, 17, 2, use_qk_norm=False)

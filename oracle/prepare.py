@@ -50,3 +50,24 @@ def decode_prepare_explicit(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, k
             kc[b, L - 1] = k[b]
             vc[b, L - 1] = v[b]
     return q, kc, vc
+
+
+def prefill_prepare_explicit(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: Optional[torch.Tensor],
+                             sin: Optional[torch.Tensor], pos0: int, qk_norm: bool, eps: float = 1e-6):
+    """fp32 reference of torch.ops.vats.prefill_prepare: q, k [N,T,heads,hd] normalised and rotated at positions
+    pos0 .. pos0+T-1 (the reference's RoPE.forward with the drop-in's position offset), v unchanged."""
+    q, k, v = q.float(), k.float(), v.float()
+    if qk_norm:
+        q = torch.nn.functional.normalize(q, p=2, dim=-1, eps=eps)
+        k = torch.nn.functional.normalize(k, p=2, dim=-1, eps=eps)
+    if cos is not None:
+        T = q.size(1)
+        c = cos[pos0:pos0 + T][None, :, None, :]
+        s = sin[pos0:pos0 + T][None, :, None, :]
+
+        def rot(x):
+            x1, x2 = x[..., ::2], x[..., 1::2]
+            return torch.stack([x1 * c - x2 * s, x1 * s + x2 * c], dim=-1).flatten(-2)
+
+        q, k = rot(q), rot(k)
+    return q, k, v

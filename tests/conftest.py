@@ -26,11 +26,15 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_files():
     """Module-level fixtures (reference module run + captured SDPA calls); the prepare_* fixtures are listed apart."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith("prepare_"))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith("prepare"))
 
 
 def prepare_golden_files():
     return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith("prepare_"))
+
+
+def prepare_seq_golden_files():
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith("prepareseq_"))
 
 
 def load_golden(name):

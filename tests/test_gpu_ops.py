@@ -407,3 +407,45 @@ def test_few_query_tokens_against_many_keys(N, Tq, Tk):
     dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
     assert _ffi.prefill_plan(N, Tq, Tk, H, G, hd, s(dq), s(dk), s(dv), s(dq), dq.data_ptr(), dk.data_ptr(),
                              dv.data_ptr()) == TC
+
+
+# ---- fused prefill pre-core producers (qk-norm + RoPE + bf16 + TMA-addressable layout), SURVEY §8f rank 1
+from conftest import prepare_seq_golden_files  # noqa: E402
+from oracle import prefill_prepare_explicit  # noqa: E402
+
+
+@pytest.mark.parametrize("name", prepare_seq_golden_files())
+def test_prefill_prepare_matches_reference_fixture(name):
+    fx = load_golden(name)
+    cos, sin = rope_tables(fx["hd"], fx["theta"], fx["T"])
+    v = torch.randn_like(fx["k_in"])
+    q, k, v2 = ops.prefill_prepare_views(fx["q_in"].cuda(), fx["k_in"].cuda(), v.cuda(), cos.cuda(), sin.cuda(), 0,
+                                         fx["use_qk_norm"])
+    torch.cuda.synchronize()
+    assert (q.float().cpu() - fx["q_out"]).abs().max() <= 2 ** -8 * fx["q_out"].abs().max()
+    assert (k.float().cpu() - fx["k_out"]).abs().max() <= 2 ** -8 * fx["k_out"].abs().max()
+    assert torch.equal(v2.cpu(), v.bfloat16())
+    assert q.stride(2) % 8 == 0 and q.stride(3) == 1      # TMA-addressable head stride (hd 60 -> 64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("N,T,H,G,hd,pos0", [(2, 300, 8, 2, 128, 0), (3, 77, 6, 2, 60, 11), (5, 8, 8, 4, 66, 0),
+                                             (1, 1, 4, 4, 16, 500)])
+def test_prefill_prepare_matches_oracle_and_feeds_attention(N, T, H, G, hd, pos0, dtype):
+    g = torch.Generator().manual_seed(41)
+    # strided views of a fused projection output, as the modules hand them over
+    qkv = torch.randn(N, T, (H + 2 * G) * hd, generator=g).to(dtype)
+    q, k, v = (t.view(N, T, -1, hd) for t in torch.split(qkv, [H * hd, G * hd, G * hd], dim=-1))
+    cos, sin = rope_tables(hd, 10000.0, pos0 + T)
+    dqkv = qkv.cuda()
+    cq, ck, cv = (t.view(N, T, -1, hd) for t in torch.split(dqkv, [H * hd, G * hd, G * hd], dim=-1))
+    dq, dk, dv = ops.prefill_prepare_views(cq, ck, cv, cos.cuda(), sin.cuda(), pos0, True)
+    torch.cuda.synchronize()
+    q_ref, k_ref, v_ref = prefill_prepare_explicit(q, k, v, cos, sin, pos0, True)
+    assert (dq.float().cpu() - q_ref).abs().max() <= 2 ** -8 + 1e-6
+    assert (dk.float().cpu() - k_ref).abs().max() <= 2 ** -8 + 1e-6
+    assert torch.equal(dv.cpu(), v_ref.bfloat16())
+    o = ops.gqa_swa_prefill(dq, dk, dv, None, None, hd ** -0.5, True, 64, 0, AUTO)
+    torch.cuda.synchronize()
+    ref = oracle_prefill(dq.cpu(), dk.cpu(), dv.cpu(), hd ** -0.5, True, 64, 0)
+    check_close(o, ref, "attention after prefill_prepare")

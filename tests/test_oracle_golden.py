@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from conftest import golden_files, load_golden, prepare_golden_files
+from conftest import golden_files, load_golden, prepare_golden_files, prepare_seq_golden_files
 from oracle import expand_kv, mask_predicate, sdpa_explicit
 
 
@@ -131,3 +131,15 @@ def test_prepare_oracle_matches_reference_producers(name):
     assert torch.allclose(q_out, fx["q_out"], atol=2e-6, rtol=0)
     assert torch.allclose(kc2[:, P], fx["k_out"], atol=2e-6, rtol=0)
     assert torch.equal(vc2[:, P], v_in) and torch.count_nonzero(kc2[:, :P]) == 0
+
+
+@pytest.mark.parametrize("name", prepare_seq_golden_files())
+def test_prefill_prepare_oracle_matches_reference_producers(name):
+    """apply_qk_norm + RoPE.forward of the reference over a whole sequence == oracle.prefill_prepare_explicit."""
+    from oracle import prefill_prepare_explicit, rope_tables
+    fx = load_golden(name)
+    cos, sin = rope_tables(fx["hd"], fx["theta"], fx["T"])
+    v = torch.randn_like(fx["k_in"])
+    q, k, v2 = prefill_prepare_explicit(fx["q_in"], fx["k_in"], v, cos, sin, 0, fx["use_qk_norm"])
+    assert torch.allclose(q, fx["q_out"], atol=2e-6, rtol=0) and torch.allclose(k, fx["k_out"], atol=2e-6, rtol=0)
+    assert torch.equal(v2, v)

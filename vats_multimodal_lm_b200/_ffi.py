@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "vats_attn_decode",
     "vats_attn_decode_workspace_bytes",
     "vats_attn_decode_prepare",
+    "vats_attn_prefill_prepare",
     "vats_attn_last_launch_count",
     "vats_attn_debug_mask",
     "vats_attn_debug_tile_range",
@@ -81,6 +82,9 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_decode_prepare.restype = i
         lib.vats_attn_decode_prepare.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, p3, p3, p3, p3, p3, p3,
                                                  i, f, vp]
+        lib.vats_attn_prefill_prepare.restype = i
+        lib.vats_attn_prefill_prepare.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, p3, p3,
+                                                  i, f, vp]
         lib.vats_attn_last_launch_count.restype = i
         lib.vats_attn_last_launch_count.argtypes = []
         lib.vats_attn_debug_mask.restype = i
@@ -152,6 +156,16 @@ def decode_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, q
         q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_cache_ptr, v_cache_ptr, seq_lens_ptr, cos_ptr,
         sin_ptr, B, H, G, hd, S_max, _i64x2(*qin_strides), _i64x2(*kin_strides), _i64x2(*vin_strides),
         _i64x2(*qout_strides), _i64x3(*k_strides), _i64x3(*v_strides), int(bool(qk_norm)), float(eps), stream))
+
+
+def prefill_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, q_out_ptr: int, k_out_ptr: int,
+                    v_out_ptr: int, cos_ptr: Optional[int], sin_ptr: Optional[int], N: int, T: int, H: int, G: int,
+                    hd: int, pos0: int, qin_strides, kin_strides, vin_strides, qout_strides, kout_strides, vout_strides,
+                    qk_norm: bool, eps: float, stream: int) -> None:
+    _check(load().vats_attn_prefill_prepare(
+        q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_out_ptr, v_out_ptr, cos_ptr, sin_ptr, N, T, H, G,
+        hd, pos0, _i64x3(*qin_strides), _i64x3(*kin_strides), _i64x3(*vin_strides), _i64x3(*qout_strides),
+        _i64x3(*kout_strides), _i64x3(*vout_strides), int(bool(qk_norm)), float(eps), stream))
 
 
 def debug_mask(out_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int], N: int, Tq: int, Tk: int,

@@ -112,3 +112,100 @@ __global__ void __launch_bounds__(kPrepareWarps * 32) decode_prepare_kernel(cons
 }
 
 }  // namespace vats
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same producers for a whole prefill chunk (prefill half, 1-D RoPE): q, k [N, T, heads, hd] are
+// L2-normalised and rotated at position pos0 + t, v is passed through; everything is rounded to bf16 once and written
+// with a caller-chosen head stride (the TMA-addressable layout: head stride rounded up to 8 elements), replacing the
+// normalise / rotate / cast / pad passes of the PyTorch path with one launch.
+namespace vats {
+
+struct PrefillPrepareParams {
+  const void* q_in;   // [N, T, H, hd]  (bf16 or fp32)
+  const void* k_in;   // [N, T, G, hd]
+  const void* v_in;
+  int in_fp32;
+  __nv_bfloat16* q_out;   // [N, T, H, hd] with strides (qo_n, qo_t, qo_h)
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* v_out;
+  const float* cos_table;  // [>= pos0 + T, hd/2] or NULL
+  const float* sin_table;
+  int N, T, H, G, hd, pos0;
+  long long qi_n, qi_t, qi_h, ki_n, ki_t, ki_h, vi_n, vi_t, vi_h;
+  long long qo_n, qo_t, qo_h, ko_n, ko_t, ko_h, vo_n, vo_t, vo_h;
+  int qk_norm;
+  float eps;
+};
+
+__global__ void __launch_bounds__(kPrepareWarps * 32) prefill_prepare_kernel(const PrefillPrepareParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_tok = p.H + 2 * p.G;
+  const long long total = (long long)p.N * p.T * rows_per_tok;
+  const long long warps = (long long)gridDim.x * kPrepareWarps;
+  const int half = (p.hd + 1) >> 1;
+  for (long long row = (long long)blockIdx.x * kPrepareWarps + warp; row < total; row += warps) {
+    const long long nt = row / rows_per_tok;
+    const int rr = (int)(row - nt * rows_per_tok);
+    const long long n = nt / p.T;
+    const int t = (int)(nt - n * p.T);
+    const void* src;
+    long long src_off;
+    __nv_bfloat16* dst;
+    bool rotate;
+    if (rr < p.H) {
+      src = p.q_in; src_off = n * p.qi_n + (long long)t * p.qi_t + (long long)rr * p.qi_h;
+      dst = p.q_out + n * p.qo_n + (long long)t * p.qo_t + (long long)rr * p.qo_h;
+      rotate = true;
+    } else if (rr < p.H + p.G) {
+      const int g = rr - p.H;
+      src = p.k_in; src_off = n * p.ki_n + (long long)t * p.ki_t + (long long)g * p.ki_h;
+      dst = p.k_out + n * p.ko_n + (long long)t * p.ko_t + (long long)g * p.ko_h;
+      rotate = true;
+    } else {
+      const int g = rr - p.H - p.G;
+      src = p.v_in; src_off = n * p.vi_n + (long long)t * p.vi_t + (long long)g * p.vi_h;
+      dst = p.v_out + n * p.vo_n + (long long)t * p.vo_t + (long long)g * p.vo_h;
+      rotate = false;
+    }
+    float x0[kPrepareMaxPairs], x1[kPrepareMaxPairs];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < kPrepareMaxPairs; ++u) {
+      const int i = lane + 32 * u;
+      x0[u] = 0.f;
+      x1[u] = 0.f;
+      if (i < half) {
+        x0[u] = prepare_load(src, src_off + 2 * i, p.in_fp32);
+        if (2 * i + 1 < p.hd) x1[u] = prepare_load(src, src_off + 2 * i + 1, p.in_fp32);
+        ss += x0[u] * x0[u] + x1[u] * x1[u];
+      }
+    }
+    float scale = 1.f;
+    if (rotate && p.qk_norm) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      scale = 1.f / fmaxf(sqrtf(ss), p.eps);
+    }
+    const bool rope = rotate && p.cos_table != nullptr;
+    const long long pos = (long long)p.pos0 + t;
+#pragma unroll
+    for (int u = 0; u < kPrepareMaxPairs; ++u) {
+      const int i = lane + 32 * u;
+      if (i < half) {
+        float a = x0[u] * scale, c = x1[u] * scale;
+        if (rope) {
+          const float cs = p.cos_table[pos * (p.hd >> 1) + i];
+          const float sn = p.sin_table[pos * (p.hd >> 1) + i];
+          const float ra = a * cs - c * sn;
+          const float rc = a * sn + c * cs;
+          a = ra;
+          c = rc;
+        }
+        dst[2 * i] = __float2bfloat16(a);
+        if (2 * i + 1 < p.hd) dst[2 * i + 1] = __float2bfloat16(c);
+      }
+    }
+  }
+}
+
+}  // namespace vats

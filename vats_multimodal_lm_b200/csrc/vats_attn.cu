@@ -713,6 +713,54 @@ int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd, const in
   return choose_kernel(A, &pl);
 }
 
+int vats_attn_prefill_prepare(const void* q_in, const void* k_in, const void* v_in, int in_dtype, void* q_out,
+                              void* k_out, void* v_out, const float* cos_table, const float* sin_table, int N, int T,
+                              int H, int G, int hd, int pos0, const int64_t qin_strides[3],
+                              const int64_t kin_strides[3], const int64_t vin_strides[3],
+                              const int64_t qout_strides[3], const int64_t kout_strides[3],
+                              const int64_t vout_strides[3], int qk_norm, float eps, void* stream) {
+  g_launches = 0;
+  if (N < 0 || T < 0 || pos0 < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
+  if (H <= 0 || G <= 0 || hd <= 0) return fail(VATS_ERR_INVALID_ARGUMENT, "H, G, hd must be positive");
+  if (in_dtype != 0 && in_dtype != 1) return fail(VATS_ERR_INVALID_ARGUMENT, "in_dtype must be 0 (bf16) or 1 (fp32)");
+  if (!qin_strides || !kin_strides || !vin_strides || !qout_strides || !kout_strides || !vout_strides)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "stride arrays must not be NULL");
+  if ((cos_table == nullptr) != (sin_table == nullptr))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "cos_table and sin_table must both be given or both be NULL");
+  if (cos_table != nullptr && hd % 2 != 0) return fail(VATS_ERR_UNSUPPORTED, "RoPE needs an even head_dim (got %d)", hd);
+  if (hd > 2 * 32 * vats::kPrepareMaxPairs) return fail(VATS_ERR_UNSUPPORTED, "head_dim %d > 256 is not supported", hd);
+  if (!(eps >= 0.f)) return fail(VATS_ERR_INVALID_ARGUMENT, "eps must be >= 0");
+  int rc = check_device();
+  if (rc != VATS_OK) return rc;
+  if (N == 0 || T == 0) return VATS_OK;
+  if (!q_in || !k_in || !v_in || !q_out || !k_out || !v_out)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "tensor pointers must not be NULL");
+  vats::PrefillPrepareParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.q_in = q_in; p.k_in = k_in; p.v_in = v_in; p.in_fp32 = in_dtype;
+  p.q_out = reinterpret_cast<__nv_bfloat16*>(q_out);
+  p.k_out = reinterpret_cast<__nv_bfloat16*>(k_out);
+  p.v_out = reinterpret_cast<__nv_bfloat16*>(v_out);
+  p.cos_table = cos_table; p.sin_table = sin_table;
+  p.N = N; p.T = T; p.H = H; p.G = G; p.hd = hd; p.pos0 = pos0;
+  p.qi_n = qin_strides[0]; p.qi_t = qin_strides[1]; p.qi_h = qin_strides[2];
+  p.ki_n = kin_strides[0]; p.ki_t = kin_strides[1]; p.ki_h = kin_strides[2];
+  p.vi_n = vin_strides[0]; p.vi_t = vin_strides[1]; p.vi_h = vin_strides[2];
+  p.qo_n = qout_strides[0]; p.qo_t = qout_strides[1]; p.qo_h = qout_strides[2];
+  p.ko_n = kout_strides[0]; p.ko_t = kout_strides[1]; p.ko_h = kout_strides[2];
+  p.vo_n = vout_strides[0]; p.vo_t = vout_strides[1]; p.vo_h = vout_strides[2];
+  p.qk_norm = qk_norm ? 1 : 0;
+  p.eps = eps;
+  const long long rows = (long long)N * T * (H + 2 * G);
+  long long blocks = (rows + vats::kPrepareWarps - 1) / vats::kPrepareWarps;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  vats::prefill_prepare_kernel<<<(unsigned)blocks, vats::kPrepareWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  return VATS_OK;
+}
+
 int vats_attn_decode_prepare(const void* q_in, const void* k_in, const void* v_in, int in_dtype, void* q_out,
                              void* k_cache, void* v_cache, const int32_t* seq_lens, const float* cos_table,
                              const float* sin_table, int B, int H, int G, int hd, int S_max,

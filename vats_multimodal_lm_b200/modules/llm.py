@@ -240,12 +240,18 @@ class Attention(nn.Module):
                 cache_out = {"k": k_all[:, past:past + 1].to(x.dtype), "v": v_all[:, past:past + 1].to(x.dtype)}
                 return self.w_o(o.to(x.dtype).reshape(B, 1, self.d_model)), cache_out
 
-        if use_qk_norm:
-            q, k = apply_qk_norm(q, k)
-
         past = kv_cache.layer_seq_len(layer_idx) if (cached and kv_cache.cache is not None) else 0
-        q = self.rope(q, offset=past)
-        k = self.rope(k, offset=past)
+        fused = x.is_cuda and hd % 2 == 0 and q.dtype in (torch.float32, torch.bfloat16)
+        if fused:
+            # qk-norm + RoPE (positions past .. past+T-1) + bf16 rounding + TMA-addressable layout in ONE launch
+            # (reference :467-474 does this with ~12 elementwise passes); the results feed the op directly
+            cos, sin = self.rope.get_cos_sin_cache(past + T)
+            q, k, v = ops.prefill_prepare_views(q, k, v, cos, sin, past, bool(use_qk_norm), 1e-6)
+        else:
+            if use_qk_norm:
+                q, k = apply_qk_norm(q, k)
+            q = self.rope(q, offset=past)
+            k = self.rope(k, offset=past)
 
         if padding_mask is not None:
             if padding_mask.shape != (B, T):
@@ -253,7 +259,14 @@ class Attention(nn.Module):
             padding_mask = padding_mask.bool()
 
         left, right = self._windows(left_window, right_window, causal)
-        cache_out = {"k": k, "v": v} if use_cache else None
+        cache_out = {"k": k.to(x.dtype), "v": v.to(x.dtype)} if use_cache else None
+
+        def core(q_, k_, v_):
+            if fused:   # already bf16 in the kernels' layout: no second cast / pad pass
+                return ops.gqa_swa_prefill(q_, k_, v_, padding_mask, None, float(self.softmax_scale), bool(causal),
+                                           int(left), int(right)).to(x.dtype)
+            return attention_core(q_, k_, v_, scale=self.softmax_scale, causal=causal, left=left, right=right,
+                                  q_valid=padding_mask, out_dtype=x.dtype)
 
         if cached:
             # intended contract of reference :508-516 — append at the layer's length, attend the cache
@@ -268,12 +281,10 @@ class Attention(nn.Module):
                 o = ops.gqa_swa_decode(q[:, 0].to(torch.bfloat16), k_all, v_all, seq_lens, float(self.softmax_scale),
                                        left).to(x.dtype)[:, None]
             else:
-                o = attention_core(q, k_all[:, :total], v_all[:, :total], scale=self.softmax_scale, causal=causal,
-                                   left=left, right=right, q_valid=padding_mask, out_dtype=x.dtype)
+                o = core(q, k_all[:, :total], v_all[:, :total])
         else:
             # reference SDPA-path semantics: padding masks QUERY rows (src/optimized_attention.py:673-675)
-            o = attention_core(q, k, v, scale=self.softmax_scale, causal=causal, left=left, right=right,
-                               q_valid=padding_mask, out_dtype=x.dtype)
+            o = core(q, k, v)
         return self.w_o(o.reshape(B, T, self.d_model)), cache_out
 
 

@@ -12,13 +12,13 @@ device in bf16; anything else raises — there is deliberately no eager / CPU pa
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional
 
 import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -196,6 +196,60 @@ def _(q, k, v, k_cache, v_cache, seq_lens, cos, sin, qk_norm, eps):
     return q.new_empty(q.shape, dtype=torch.bfloat16)
 
 
+@torch.library.custom_op("vats::prefill_prepare", mutates_args=(), device_types="cuda")
+def prefill_prepare(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: Optional[torch.Tensor],
+                    sin: Optional[torch.Tensor], pos0: int, qk_norm: bool, eps: float) -> List[torch.Tensor]:
+    """Fused pre-core producers of a prefill chunk: qk L2-norm + 1-D RoPE at positions pos0 .. pos0+T-1 + bf16 rounding,
+    written in the TMA-addressable layout (head stride rounded up to 8 elements; sequences of <= 32 tokens stay
+    dense for the short-sequence kernel).  q [N,T,H,hd], k/v [N,T,G,hd] (bf16 or fp32, any strides with a contiguous
+    head_dim), cos/sin [>= pos0+T, hd/2] fp32 or None.  Returns the three padded buffers [N,T,heads,hd_pad]; slice
+    `[..., :hd]` to get q', k', v' (`prefill_prepare_views` does)."""
+    if q.dim() != 4 or k.dim() != 4 or v.shape != k.shape or q.shape[:2] != k.shape[:2] or q.size(3) != k.size(3):
+        raise ValueError("q must be [N,T,H,hd]; k and v must be [N,T,G,hd]")
+    if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("q, k, v must share one dtype, bf16 or fp32")
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("prefill_prepare needs CUDA tensors (no CPU fallback)")
+    N, T, H, hd = q.shape
+    G = k.size(2)
+    if (cos is None) != (sin is None):
+        raise ValueError("cos and sin must both be given or both be None")
+    if cos is not None:
+        if cos.dtype != torch.float32 or sin.dtype != torch.float32 or cos.shape != sin.shape or cos.dim() != 2 or \
+                cos.size(1) != hd // 2 or hd % 2 != 0 or cos.size(0) < pos0 + T:
+            raise ValueError("cos / sin must be fp32 [>= pos0 + T, hd/2] tables")
+        cos, sin = cos.contiguous(), sin.contiguous()
+    q, k, v = _rowmajor_last(q), _rowmajor_last(k), _rowmajor_last(v)
+    hp = hd if (hd % 8 == 0 or T <= 32) else (hd + 7) // 8 * 8
+    bufs = [torch.empty((N, T, heads, hp), dtype=torch.bfloat16, device=q.device) for heads in (H, G, G)]
+    if q.numel() == 0:
+        return bufs
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.prefill_prepare(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.dtype == torch.float32, bufs[0].data_ptr(),
+                             bufs[1].data_ptr(), bufs[2].data_ptr(), cos.data_ptr() if cos is not None else None,
+                             sin.data_ptr() if sin is not None else None, N, T, H, G, hd, int(pos0), q.stride()[:3],
+                             k.stride()[:3], v.stride()[:3], bufs[0].stride()[:3], bufs[1].stride()[:3],
+                             bufs[2].stride()[:3], qk_norm, eps, stream)
+    return bufs
+
+
+@prefill_prepare.register_fake
+def _(q, k, v, cos, sin, pos0, qk_norm, eps):
+    hd, T = q.size(3), q.size(1)
+    hp = hd if (hd % 8 == 0 or T <= 32) else (hd + 7) // 8 * 8
+    return [t.new_empty((*t.shape[:3], hp), dtype=torch.bfloat16) for t in (q, k, v)]
+
+
+def prefill_prepare_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: Optional[torch.Tensor],
+                          sin: Optional[torch.Tensor], pos0: int, qk_norm: bool, eps: float = 1e-6):
+    """`vats::prefill_prepare`, returning q', k', v' as [..., :hd] views of the padded buffers (what `gqa_swa_prefill`
+    takes: the head stride keeps rows 16-byte aligned for TMA)."""
+    hd = q.size(3)
+    qb, kb, vb = prefill_prepare(q, k, v, cos, sin, pos0, qk_norm, eps)
+    return qb[..., :hd], kb[..., :hd], vb[..., :hd]
+
+
 def attn_mask(q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], N: int, Tq: int, Tk: int,
               causal: bool, left: int, right: int, device: Optional[torch.device] = None) -> torch.Tensor:
     """The kernels' own mask predicate, materialised (uint8 [N,Tq,Tk]); used for the bit-exact mask tests."""
@@ -228,3 +282,4 @@ def _no_cpu(name):
 gqa_swa_prefill.register_kernel("cpu")(_no_cpu("gqa_swa_prefill"))
 gqa_swa_decode.register_kernel("cpu")(_no_cpu("gqa_swa_decode"))
 decode_prepare.register_kernel("cpu")(_no_cpu("decode_prepare"))
+prefill_prepare.register_kernel("cpu")(_no_cpu("prefill_prepare"))
