@@ -129,8 +129,33 @@ def prepare_seq_case(name, seed, H, G, hd, theta, T, B, use_qk_norm=True):
     print(name, tuple(qr.shape))
 
 
+def cross_case(name, seed, d_model, H, B, Tq, Tk, pad):
+    """Image-generation cross-attention block (queries = image tokens, keys / values = text tokens, key padding)."""
+    m = ref.imagegen_cross()
+    torch.manual_seed(seed)
+    hd = d_model // H
+    blk = m.CrossAttentionBlock(d_model, H, 1.0 / hd ** 0.5, False, 1e-7, 0.0).eval()
+    x = torch.randn(B, Tq, d_model)
+    text = torch.randn(B, Tk, d_model)
+    padding_mask = None
+    if pad:
+        padding_mask = torch.rand(B, Tk) > 0.3
+        padding_mask[:, 0] = True
+    with torch.no_grad(), ref.capture_sdpa(m) as calls:
+        out = blk(x, text, padding_mask)
+    torch.save({
+        "kind": "cross", "ctor": dict(d_model=d_model, num_heads=H, softmax_scale=1.0 / hd ** 0.5, use_proj_bias=False,
+                                      eps=1e-7, dropout=0.0),
+        "state_dict": {k: v.clone() for k, v in blk.state_dict().items()},
+        "x": x, "text": text, "padding_mask": padding_mask, "sdpa_calls": _pack_calls(calls), "out": out,
+    }, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), len(calls), "sdpa call(s)")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    cross_case("cross_hd16_pad", 501, 128, 8, 2, 150, 16, True)
+    cross_case("cross_hd64", 502, 128, 2, 1, 40, 70, False)
     prepare_seq_case("prepareseq_hd60_t40", 403, 6, 2, 60, 10000.0, 40, 2)
     # pre-core step of a decode token (qk-norm + RoPE at position P)
     prepare_case("prepare_hd128_p300", 401, 8, 2, 128, 10000.0, 300, 3)

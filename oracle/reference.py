@@ -47,6 +47,13 @@ def vit3d():
     return m
 
 
+def imagegen_cross():
+    """reference src/autoregressive_image_gen/autoregressive_transformer/attention/cross_attention.py"""
+    _ensure_path()
+    import src.autoregressive_image_gen.autoregressive_transformer.attention.cross_attention as m
+    return m
+
+
 @contextlib.contextmanager
 def capture_sdpa(module) -> "contextlib.AbstractContextManager[List[Dict[str, Any]]]":
     """Record every `F.scaled_dot_product_attention` call the reference module makes: the tensors entering the

@@ -26,7 +26,11 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_files():
     """Module-level fixtures (reference module run + captured SDPA calls); the prepare_* fixtures are listed apart."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith("prepare"))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith(("prepare", "cross_")))
+
+
+def cross_golden_files():
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith("cross_"))
 
 
 def prepare_golden_files():

@@ -218,3 +218,19 @@ def test_vit2d_reference_attention_tests_rerun_on_dropin():
     for b in (1, 2, 4, 8, 16, 32, 64):
         y = attn(torch.randn(b, T, d, device=dev), False, True, -1, -1)
         assert y.shape == (b, T, d) and torch.isfinite(y).all()
+
+
+from conftest import cross_golden_files  # noqa: E402
+
+
+@pytest.mark.parametrize("name", cross_golden_files())
+def test_cross_attention_block_matches_reference_fixture(name):
+    """SURVEY §8f rank 3, first call site: the image-gen CrossAttentionBlock drop-in (Tq != Tk, key padding, MHA) with
+    the reference's state_dict reproduces the reference block's output."""
+    fx = load_golden(name)
+    blk = vl.CrossAttentionBlock(**fx["ctor"]).cuda().eval()
+    blk.load_state_dict(fx["state_dict"])
+    pm = None if fx["padding_mask"] is None else fx["padding_mask"].cuda()
+    with torch.no_grad():
+        out = blk(fx["x"].cuda(), fx["text"].cuda(), pm)
+    _close(out.cpu(), fx["out"], f"cross block {name}")

@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from conftest import golden_files, load_golden, prepare_golden_files, prepare_seq_golden_files
+from conftest import cross_golden_files, golden_files, load_golden, prepare_golden_files, prepare_seq_golden_files
 from oracle import expand_kv, mask_predicate, sdpa_explicit
 
 
@@ -143,3 +143,25 @@ def test_prefill_prepare_oracle_matches_reference_producers(name):
     q, k, v2 = prefill_prepare_explicit(fx["q_in"], fx["k_in"], v, cos, sin, 0, fx["use_qk_norm"])
     assert torch.allclose(q, fx["q_out"], atol=2e-6, rtol=0) and torch.allclose(k, fx["k_out"], atol=2e-6, rtol=0)
     assert torch.equal(v2, v)
+
+
+@pytest.mark.parametrize("name", cross_golden_files())
+def test_oracle_matches_reference_cross_attention_call(name):
+    """Image-gen cross-attention (reference cross_attention.py:73-101): key-padding mask == predicate with k_valid,
+    SDPA output == oracle.sdpa_explicit with the reference's softmax_scale."""
+    fx = load_golden(name)
+    (call,) = fx["sdpa_calls"]
+    q = call["q"].permute(0, 2, 1, 3).contiguous()
+    k = call["k"].permute(0, 2, 1, 3).contiguous()
+    v = call["v"].permute(0, 2, 1, 3).contiguous()
+    N, Tq, H, hd = q.shape
+    Tk = k.size(1)
+    assert call["scale"] == fx["ctor"]["softmax_scale"] and not call["is_causal"]
+    pm = fx["padding_mask"]
+    mask = mask_predicate(N, Tq, Tk, False, -1, -1, k_valid=pm)
+    if pm is None:
+        assert call["attn_mask"] is None
+    else:
+        assert torch.equal(call["attn_mask"].expand(N, 1, Tq, Tk)[:, 0], mask)
+    out = sdpa_explicit(q, k, v, mask, call["scale"])
+    assert torch.allclose(out, call["out"].permute(0, 2, 1, 3), atol=2e-6, rtol=0)

@@ -5,7 +5,8 @@ drop-in modules that keep the reference's signatures.  No CPU path: importing wo
 from . import _ffi, ops  # noqa: F401  (ops registers torch.ops.vats.*)
 from .modules import (  # noqa: F401
     Attention, AttentionBlock, KVCache, RMSNorm, RoPE, RoPE2D, RoPE3D, SpatialAttention, SpatialAttentionBlock,
-    SpatioTemporalAttention, SpatioTemporalAttentionBlock, get_default_window_mode, set_default_window_mode,
+    SpatioTemporalAttention, SpatioTemporalAttentionBlock, CrossAttention, CrossAttentionBlock,
+    get_default_window_mode, set_default_window_mode,
 )
 from .ops import gqa_swa_decode, gqa_swa_prefill  # noqa: F401
 
