@@ -158,7 +158,10 @@ def test_vit3d_temporal_and_tiny_head_dim_simt():
 
 # (N, Tq, Tk, H, G, hd): the one-CTA-per-sequence kernel (Tk <= 32): bulk (dense, odd hd/2) and cp.async staging, every
 # keys-per-pass / heads-per-thread instantiation, Tq != Tk, more sequences than persistent CTAs
+# (the last three: more query tokens than fit one stage -> several work items per sequence; image-gen cross-attention
+#  geometry: thousands of image tokens against 16 text tokens)
 SHORT_SHAPES = [
+    (3, 700, 8, 32, 8, 66), (2, 3000, 16, 8, 8, 16), (2, 1000, 31, 6, 3, 34),
     (700, 8, 8, 32, 8, 66), (5, 8, 8, 8, 2, 64), (4, 16, 16, 6, 3, 34), (3, 32, 32, 4, 4, 20), (9, 5, 8, 12, 4, 26),
     (6, 8, 3, 16, 2, 66), (2, 30, 17, 3, 3, 10), (11, 1, 1, 8, 8, 66), (3, 12, 12, 10, 5, 18), (2, 7, 7, 6, 6, 128),
 ]

@@ -39,19 +39,22 @@ struct ShortParams {
   PrefillParams a;
   int hd2;        // head_dim / 2: 32-bit words per row
   int pitch;      // words per staged row
-  int q_rows;     // Tq * H
+  int q_rows;     // tq_chunk * H: query rows of a full work item
+  int tq_chunk;   // query tokens per work item (== Tq unless the Q block of a sequence does not fit a stage)
+  int chunks;     // ceil(Tq / tq_chunk): work items per sequence; item = sequence * chunks + chunk
+  long long num_items;   // N * chunks
   int kv_rows;    // Tk * G
   int q_words;    // staged words per sequence and stage: Q/O block, K block, V block (multiples of 4)
   int kv_words;
   int vt_words;   // per compute warp: nss * 32 * KMAX / 2 words of transposed V (its group's B operand of P.V)
   int nss;        // ceil(hd2 / 16): 16-word (32-column) super-steps of head_dim
-  int m_rows;     // Tq * hpg: query rows per KV group
+  int m_rows;     // tq_chunk * hpg: query rows per KV group in a full work item
   int m_blocks;   // ceil(m_rows / 32): 32-row blocks per group; units = G * m_blocks, one warp each
   int o_bulk;     // O[n] is one contiguous 16-byte aligned block: bulk store
   int stages;     // shared-memory ring depth (2..4) and how many sequences ahead the loads run (1 .. stages - 1)
   int dist;
   int no_mask;    // every (query, key) pair is allowed: skip the predicate
-  unsigned div_H[2], div_G[2], div_hpg[2], div_mb[2], div_hd2[2];  // magic numbers (tc_fastdiv)
+  unsigned div_H[2], div_G[2], div_hpg[2], div_mb[2], div_hd2[2], div_chunks[2];  // magic numbers (tc_fastdiv)
   unsigned long long* trace;   // debug (-DVATS_ENABLE_TRACE): thread 0 of block 0 appends (tag, clock64) pairs
   int trace_cap;
 };
@@ -118,24 +121,43 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
   }
   __syncthreads();
 
-  auto issue_load = [&](long long n, int s) {
+  // work item -> (sequence n, first query token t0, query tokens nt)
+  auto item_of = [&](long long item, long long* n, int* t0, int* ntok) {
+    long long seq = item;
+    int c = 0;
+    if (P.chunks > 1) {
+      unsigned qq, rr;
+      short_fastdiv((unsigned)item, P.div_chunks, (unsigned)P.chunks, &qq, &rr);
+      seq = qq;
+      c = (int)rr;
+    }
+    *n = seq;
+    *t0 = c * P.tq_chunk;
+    *ntok = min(P.tq_chunk, a.Tq - c * P.tq_chunk);
+  };
+
+  auto issue_load = [&](long long item, int s) {
+    long long n;
+    int t0, ntok;
+    item_of(item, &n, &t0, &ntok);
+    const int q_rows = ntok * a.H;
     const uint32_t sq = smem_u32(smem_w + (size_t)s * stage_words);
     const uint32_t sk = sq + (uint32_t)P.q_words * 4u, sv = sk + (uint32_t)P.kv_words * 4u;
     const uint32_t bar = smem_u32(&full[s]);
     if (kBulk) {
       if (io_lane) {
-        const uint32_t qb = (uint32_t)P.q_rows * (uint32_t)P.hd2 * 4u, kb = (uint32_t)P.kv_rows * (uint32_t)P.hd2 * 4u;
+        const uint32_t qb = (uint32_t)q_rows * (uint32_t)P.hd2 * 4u, kb = (uint32_t)P.kv_rows * (uint32_t)P.hd2 * 4u;
         mbar_expect_tx(bar, qb + 2u * kb);
-        bulk_load_1d(sq, a.q + n * a.qs_n, qb, bar);
+        bulk_load_1d(sq, a.q + n * a.qs_n + (long long)t0 * a.qs_t, qb, bar);
         bulk_load_1d(sk, a.k + n * a.ks_n, kb, bar);
         bulk_load_1d(sv, a.v + n * a.vs_n, kb, bar);
       }
     } else {
       // one warp per row; lanes walk the row's 32-bit words
-      for (int row = warp; row < P.q_rows; row += nwarps) {
+      for (int row = warp; row < q_rows; row += nwarps) {
         unsigned t, h;
         short_fastdiv((unsigned)row, P.div_H, (unsigned)a.H, &t, &h);
-        const __nv_bfloat16* src = a.q + n * a.qs_n + (long long)t * a.qs_t + (long long)h * a.qs_h;
+        const __nv_bfloat16* src = a.q + n * a.qs_n + (long long)(t0 + (int)t) * a.qs_t + (long long)h * a.qs_h;
         for (int w = lane; w < P.hd2; w += 32) cp_async_4(sq + (uint32_t)(row * P.pitch + w) * 4u, src + 2 * w);
       }
       for (int row = warp; row < P.kv_rows; row += nwarps) {
@@ -154,8 +176,8 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
 
   // prologue: the first `dist` sequences of this CTA
   for (int d = 0; d < P.dist; ++d) {
-    const long long n0 = (long long)blockIdx.x + (long long)d * gridDim.x;
-    if (n0 < a.N) issue_load(n0, d);
+    const long long i0 = (long long)blockIdx.x + (long long)d * gridDim.x;
+    if (i0 < P.num_items) issue_load(i0, d);
   }
 #if defined(VATS_ENABLE_TRACE)
   int trace_n = 0;
@@ -172,12 +194,17 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
   uint32_t ph = 0u;
   const int units = a.G * P.m_blocks;
   const uint32_t all_keys = a.Tk >= 32 ? 0xffffffffu : (1u << a.Tk) - 1u;
-  for (long long n = blockIdx.x; n < a.N; n += gridDim.x, ++it) {
+  for (long long item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+    long long n;
+    int t0, ntok;
+    item_of(item, &n, &t0, &ntok);
+    const int q_rows = ntok * a.H;       // rows of this item (the last chunk of a sequence may be shorter)
+    const int m_rows = ntok * a.hpg;
     // ---- prefetch the sequence `dist` ahead; its stage was last used by iteration it + dist - stages, whose bulk
     //      store must have finished reading shared memory: at most stages - dist - 1 younger stores may still be pending
     {
-      const long long nn = n + (long long)P.dist * gridDim.x;
-      if (nn < a.N) {
+      const long long nn = item + (long long)P.dist * gridDim.x;
+      if (nn < P.num_items) {
         if (kBulk && P.o_bulk && io_lane) {
           const int pend = P.stages - P.dist - 1;
           if (pend <= 0) bulk_wait_group_read<0>();
@@ -229,7 +256,7 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int r = (int)mb * 32 + mt * 16 + hf * 8 + gq;
-          rvalid[mt][hf] = r < P.m_rows;
+          rvalid[mt][hf] = r < m_rows;
           unsigned tok, hh;
           short_fastdiv((unsigned)(rvalid[mt][hf] ? r : 0), P.div_hpg, (unsigned)a.hpg, &tok, &hh);
           qrow[mt][hf] = sQ + (size_t)((int)tok * a.H + (int)g * a.hpg + (int)hh) * P.pitch;
@@ -238,11 +265,11 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
             al = 0u;
 #pragma unroll
             for (int j = 0; j < KMAX; ++j) {
-              bool ok = j < a.Tk && allowed_geom(a.mask, (int)tok, j);
+              bool ok = j < a.Tk && allowed_geom(a.mask, t0 + (int)tok, j);
               if (ok && a.k_valid != nullptr) ok = a.k_valid[n * a.Tk + j] != 0;
               al |= ok ? (1u << j) : 0u;
             }
-            if (a.q_valid != nullptr && a.q_valid[n * a.Tq + tok] == 0) al = 0u;
+            if (a.q_valid != nullptr && a.q_valid[n * a.Tq + t0 + tok] == 0) al = 0u;
           }
           allow[mt][hf] = al;
         }
@@ -367,16 +394,16 @@ __global__ void __launch_bounds__(kShortMaxThreads, 2) prefill_short_kernel(cons
       __syncthreads();
       VATS_SHORT_TRACE(5)
       if (io_lane) {
-        bulk_store_1d(a.o + n * a.os_n, smem_u32(sQ), (uint32_t)P.q_rows * (uint32_t)P.hd2 * 4u);
+        bulk_store_1d(a.o + n * a.os_n + (long long)t0 * a.os_t, smem_u32(sQ), (uint32_t)q_rows * (uint32_t)P.hd2 * 4u);
         bulk_commit_group();
       }
       VATS_SHORT_TRACE(6)
     } else {
       __syncthreads();
-      for (int row = warp; row < P.q_rows; row += nwarps) {
+      for (int row = warp; row < q_rows; row += nwarps) {
         unsigned t, h;
         short_fastdiv((unsigned)row, P.div_H, (unsigned)a.H, &t, &h);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(a.o + n * a.os_n + (long long)t * a.os_t + (long long)h * a.os_h);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a.o + n * a.os_n + (long long)(t0 + (int)t) * a.os_t + (long long)h * a.os_h);
         for (int w = lane; w < P.hd2; w += 32) dst[w] = sQ[row * P.pitch + w];
       }
       __syncthreads();   // the stage is refilled by a later iteration's prefetch
