@@ -454,6 +454,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
             issue_s(q_lo0, k_lo, tS0);
             tc_commit_pred(s_bar0, leader);
             if (last_s) tc_commit_pred(smem_u32(&bars->q_empty[0]), leader);
+          } else {
+            // tile 0 is complete: let its warpgroup start the epilogue now instead of behind tile 1's last P.V (it
+            // then runs ahead of tile 1 by that much, which also takes the two exponential phases apart)
+            tc_commit_pred(smem_u32(&bars->o_full[0]), leader);
           }
           // ---- tile 1
           if (active1) {
@@ -477,7 +481,6 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         if (leader) trace(0x140);
-        tc_commit_pred(smem_u32(&bars->o_full[0]), leader);
         ++qn[0];
         if (active1) {
           tc_commit_pred(smem_u32(&bars->o_full[1]), leader);
