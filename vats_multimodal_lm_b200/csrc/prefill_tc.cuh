@@ -52,6 +52,8 @@ struct TcParams {
                      // (tmap_o is valid); 2 = the same staging, written out with coalesced 32-bit stores (rows only
                      // 4-byte aligned, e.g. head_dim 66)
   int num_work;      // N * G * pairs * q_blocks work items, walked round-robin by the persistent CTAs
+  int no_band;       // 1: no causal mask and no window — every query block visits all ceil(Tk/128) KV tiles and only
+                     // the sequence end cuts a tile (skips the 64-bit band arithmetic every role runs per item)
   unsigned div_qb[2], div_pairs[2], div_g[2];  // magic (multiplier, shift) pairs for division by q_blocks / pairs / G
   unsigned long long* trace;  // debug: block 0 appends (tag, clock64) pairs here (NULL = off); [0] = count
   int trace_cap;
@@ -197,9 +199,14 @@ __device__ __forceinline__ TcWork tc_decode_work(const TcParams& P, int w) {
   const int hh0 = (int)pair * 2;
   k.active1 = (hh0 + 1) < a.hpg;
   k.head0 = k.g * a.hpg + hh0;
-  int t_last;
-  tile_range(a.mask, k.q0, kTcBlockM, kTcBlockN, &k.t_first, &t_last);
-  k.n_tiles = t_last - k.t_first + 1;
+  if (P.no_band) {
+    k.t_first = 0;
+    k.n_tiles = (a.Tk + kTcBlockN - 1) >> 7;
+  } else {
+    int t_last;
+    tile_range(a.mask, k.q0, kTcBlockM, kTcBlockN, &k.t_first, &t_last);
+    k.n_tiles = t_last - k.t_first + 1;
+  }
   return k;
 }
 
@@ -513,7 +520,10 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
     float m_used = -INFINITY;  // reference maximum in scaled-log2 units; -inf = not set yet
     // KV tiles [full_first, full_last] are allowed for every row of the block: no per-element predicate there
     int full_first, full_last;
-    {
+    if (P.no_band) {
+      full_first = 0;
+      full_last = (a.Tk >> 7) - 1;
+    } else {
       int q_last = q0 + kTcBlockM - 1;
       if (q_last > a.Tq - 1) q_last = a.Tq - 1;
       long long lo = key_lo(a.mask, q_last);   // tightest lower bound

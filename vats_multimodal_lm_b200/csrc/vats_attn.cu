@@ -444,6 +444,7 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.regions = (P.hd_pad + 63) / 64;
   P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
   P.pairs = (P.a.hpg + 1) / 2;
+  P.no_band = (!A.causal && A.left < 0 && A.right < 0) ? 1 : 0;
   // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
   if (any_ldg) {
@@ -461,12 +462,23 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
                   ? 1
                   : 0;
   {
-    static int order = -1;
-    if (order < 0) {
-      const char* e = getenv("VATS_PREFILL_ORDER_SOFTMAX");  // tuning knob
-      order = (e && atoi(e) == 0) ? 0 : 1;
+    // The two softmax warpgroups take turns in the exponential phase when an item visits few KV tiles (they start
+    // in lock-step there: cfg3 0.207 vs 0.225 ms); on long items they drift apart by themselves and the hand-over only
+    // costs (cfg5 1 016 vs 1 035 TFLOP/s).
+    static int order = -1;   // -1: by geometry
+    static bool read = false;
+    if (!read) {
+      const char* e = getenv("VATS_PREFILL_ORDER_SOFTMAX");  // tuning knob: 0 / 1 force
+      if (e) order = atoi(e) ? 1 : 0;
+      read = true;
     }
-    P.order_softmax = order;
+    long long tiles = (A.Tk + vats::kTcBlockN - 1) / vats::kTcBlockN;
+    if (A.left >= 0 && (A.causal || A.right >= 0)) {
+      const long long band = (long long)A.left + (A.causal ? 0 : A.right) + vats::kTcBlockM;   // keys a query block can see
+      const long long bt = band / vats::kTcBlockN + 2;
+      if (bt < tiles) tiles = bt;
+    }
+    P.order_softmax = order >= 0 ? order : (tiles <= 8 ? 1 : 0);
   }
   // ring depths: fill the 227 KB of shared memory (also pins one CTA per SM, which owns all 512 TMEM columns)
   const int tile_bytes = P.regions * vats::kTcRegionBytes;
