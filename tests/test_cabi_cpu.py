@@ -44,6 +44,38 @@ def test_argument_validation_precedes_device_check():
     assert e.value.code == 1 and "scale" in str(e.value)
 
 
+def test_prepare_entry_points_validate_before_touching_the_device():
+    """vats_attn_decode_prepare / vats_attn_prefill_prepare: argument errors are reported with code 1 (or 2 for an
+    unsupported geometry) whether or not a GPU is present; on a box without one a well-formed call fails loudly."""
+    z2, z3 = (8, 8), (8, 8, 8)
+    with pytest.raises(_ffi.VatsAttnError) as e:   # in_dtype must be 0 / 1 (raw call: the wrapper takes a bool)
+        _ffi._check(_ffi.load().vats_attn_decode_prepare(16, 16, 16, 7, 16, 16, 16, 16, None, None, 1, 2, 1, 8, 4,
+                                                          _ffi._i64x2(*z2), _ffi._i64x2(*z2), _ffi._i64x2(*z2),
+                                                          _ffi._i64x2(*z2), _ffi._i64x3(*z3), _ffi._i64x3(*z3), 1, 1e-6,
+                                                          None))
+    assert e.value.code == 1 and "in_dtype" in str(e.value)
+    with pytest.raises(_ffi.VatsAttnError) as e:   # cos without sin
+        _ffi.decode_prepare(16, 16, 16, False, 16, 16, 16, 16, 16, None, 1, 2, 1, 8, 4, z2, z2, z2, z2, z3, z3, True,
+                            1e-6, None)
+    assert e.value.code == 1 and "cos_table" in str(e.value)
+    with pytest.raises(_ffi.VatsAttnError) as e:   # RoPE needs an even head_dim
+        _ffi.prefill_prepare(16, 16, 16, True, 16, 16, 16, 16, 16, 1, 4, 2, 1, 7, 0, z3, z3, z3, z3, z3, z3, True, 1e-6,
+                             None)
+    assert e.value.code == 2 and "even head_dim" in str(e.value)
+    with pytest.raises(_ffi.VatsAttnError) as e:   # head_dim > 256
+        _ffi.prefill_prepare(16, 16, 16, True, 16, 16, 16, None, None, 1, 4, 2, 1, 300, 0, z3, z3, z3, z3, z3, z3, True,
+                             1e-6, None)
+    assert e.value.code == 2
+    if not torch.cuda.is_available():
+        with pytest.raises(_ffi.VatsAttnError) as e:
+            _ffi.prefill_prepare(16, 16, 16, True, 16, 16, 16, None, None, 1, 4, 2, 1, 8, 0, z3, z3, z3, z3, z3, z3,
+                                 True, 1e-6, None)
+        assert e.value.code in (2, 3)
+        with pytest.raises(RuntimeError):
+            torch.ops.vats.prefill_prepare(torch.zeros(1, 2, 2, 8), torch.zeros(1, 2, 1, 8), torch.zeros(1, 2, 1, 8),
+                                           None, None, 0, True, 1e-6)
+
+
 CASES = [
     # Tq, Tk, causal, left, right
     (300, 300, True, -1, -1), (300, 300, True, 64, 0), (300, 300, True, 0, 0), (300, 300, False, 40, 40),
