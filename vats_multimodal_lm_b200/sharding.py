@@ -136,7 +136,9 @@ class PeerGather:
         """Write `piece` (ready on the current stream) into out[index] of every rank, on side streams."""
         ready = torch.cuda.Event()
         ready.record()
-        for r in range(self.world):
+        # every rank starts with a different peer (own copy last), so no destination is hit by all ranks at once
+        for i in range(1, self.world + 1):
+            r = (self.rank + i) % self.world
             st = self.streams[r]
             st.wait_event(ready)
             with torch.cuda.stream(st):
