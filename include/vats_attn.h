@@ -85,6 +85,25 @@ int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o,
                          const int64_t v_strides[3], const int64_t o_strides[3],
                          float scale, int causal, int left, int right, int kernel, void* stream);
 
+/*
+ * Same, with caller-owned scratch.  Tensors whose rows TMA cannot address (head dims such as 60 or 66 in a dense
+ * layout: rows only 4- or 8-byte aligned) are streamed once into `workspace` with the head stride rounded up to 8
+ * elements and the TMA-fed kernel runs on the copies; vats_attn_prefill_workspace_bytes() says how much that takes
+ * (0 = no scratch needed).  Without a workspace (NULL / too small — what vats_attn_prefill and _ex pass) the kernel
+ * stages such rows itself with cp.async, which is slower.  The library never allocates device memory.
+ */
+int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o,
+                         const uint8_t* q_valid, const uint8_t* k_valid,
+                         int N, int Tq, int Tk, int H, int G, int hd,
+                         const int64_t q_strides[3], const int64_t k_strides[3],
+                         const int64_t v_strides[3], const int64_t o_strides[3],
+                         float scale, int causal, int left, int right, int kernel,
+                         void* workspace, size_t workspace_bytes, void* stream);
+size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, int hd,
+                                         const int64_t q_strides[3], const int64_t k_strides[3],
+                                         const int64_t v_strides[3],
+                                         const void* q, const void* k, const void* v);
+
 /* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / VATS_KERNEL_SIMT). Host only. */
 int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
                            const int64_t q_strides[3], const int64_t k_strides[3],
@@ -101,7 +120,11 @@ int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
  *             the new k,v at position seq_lens[b]-1 before the call).  The query sits at position
  *             seq_lens[b]-1 and attends keys  max(0, L-1-left) .. L-1  (left < 0 = all keys 0..L-1).
  *             seq_lens[b] == 0 gives a zero output row.
- *   workspace device scratch of at least vats_attn_decode_workspace_bytes(...) bytes (split-K partials).
+ *   workspace device scratch of at least vats_attn_decode_workspace_bytes(...) bytes: split counters (the first
+ *             bytes; they must be ZERO on entry and are left zero by every completed call, so one zero-filled buffer
+ *             serves any number of stream-ordered calls) followed by the fp32 split-K partials.  After a failed /
+ *             aborted launch re-zero it.  Head dims TMA can address — even, <= 128, cache base and strides multiples
+ *             of 16 bytes (a head stride of 64 for hd 60) — run on decode_mma_kernel; others on the CUDA-core kernel.
  */
 int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, void* o,
                      const int32_t* seq_lens,
@@ -153,6 +176,21 @@ int vats_attn_decode_prepare(const void* q_in, const void* k_in, const void* v_i
 
 /* Number of kernels the last successful vats_attn_decode / vats_attn_prefill on this thread launched. */
 int vats_attn_last_launch_count(void);
+
+/* Which kernel the last successful compute call on this thread ended in (the main kernel, not helpers such as the
+ * repack or the split combine).  Lets tests and the benchmark prove which path a call site reaches. */
+#define VATS_LAUNCHED_NONE 0
+#define VATS_LAUNCHED_PREFILL_TC 1       /* prefill_tc_kernel<false>: TMA + tcgen05 */
+#define VATS_LAUNCHED_PREFILL_TC_LDG 2   /* prefill_tc_kernel<true>: cp.async staging + tcgen05 */
+#define VATS_LAUNCHED_PREFILL_SHORT 3    /* prefill_short_kernel: <= 32 keys */
+#define VATS_LAUNCHED_PREFILL_SIMT 4     /* prefill_simt_kernel: generic CUDA-core fallback */
+#define VATS_LAUNCHED_DECODE_MMA 5       /* decode_mma_kernel: TMA + mma.sync split-K */
+#define VATS_LAUNCHED_DECODE_SPLIT 6     /* decode_split_kernel (+ decode_combine_kernel) */
+#define VATS_LAUNCHED_PREFILL_PREPARE 7
+#define VATS_LAUNCHED_DECODE_PREPARE 8
+#define VATS_LAUNCHED_PREFILL_MID 9      /* prefill_mid_kernel: 33..256 keys, K/V resident per (sequence, KV group) */
+#define VATS_LAUNCHED_BACKWARD 10        /* attention backward kernels */
+int vats_attn_last_kernel(void);
 
 /*
  * Materialise the mask predicate with the kernels' own device function: out[n,i,j] = allowed(n,i,j) as 0/1.

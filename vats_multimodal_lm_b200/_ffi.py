@@ -23,12 +23,15 @@ KERNEL_SIMT = 2
 EXPORTED_SYMBOLS = (
     "vats_attn_prefill",
     "vats_attn_prefill_ex",
+    "vats_attn_prefill_ws",
+    "vats_attn_prefill_workspace_bytes",
     "vats_attn_prefill_plan",
     "vats_attn_decode",
     "vats_attn_decode_workspace_bytes",
     "vats_attn_decode_prepare",
     "vats_attn_prefill_prepare",
     "vats_attn_last_launch_count",
+    "vats_attn_last_kernel",
     "vats_attn_debug_mask",
     "vats_attn_debug_tile_range",
     "vats_attn_debug_tile_is_full",
@@ -52,6 +55,30 @@ _lock = threading.Lock()
 _i64x3 = ctypes.c_int64 * 3
 _i64x2 = ctypes.c_int64 * 2
 
+# ctypes stride arrays are immutable inputs: build each distinct one once (the same few geometries repeat every step)
+_s3_cache: dict = {}
+_s2_cache: dict = {}
+
+
+def _s3(strides) -> "ctypes.Array":
+    key = tuple(strides)
+    arr = _s3_cache.get(key)
+    if arr is None:
+        if len(_s3_cache) > 4096:
+            _s3_cache.clear()
+        arr = _s3_cache[key] = _i64x3(*key)
+    return arr
+
+
+def _s2(strides) -> "ctypes.Array":
+    key = tuple(strides)
+    arr = _s2_cache.get(key)
+    if arr is None:
+        if len(_s2_cache) > 4096:
+            _s2_cache.clear()
+        arr = _s2_cache[key] = _i64x2(*key)
+    return arr
+
 
 def load() -> ctypes.CDLL:
     """Load the library once; raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
@@ -73,6 +100,10 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_prefill.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, vp]
         lib.vats_attn_prefill_ex.restype = i
         lib.vats_attn_prefill_ex.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp]
+        lib.vats_attn_prefill_ws.restype = i
+        lib.vats_attn_prefill_ws.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp, sz, vp]
+        lib.vats_attn_prefill_workspace_bytes.restype = sz
+        lib.vats_attn_prefill_workspace_bytes.argtypes = [i, i, i, i, i, i, p3, p3, p3, vp, vp, vp]
         lib.vats_attn_prefill_plan.restype = i
         lib.vats_attn_prefill_plan.argtypes = [i, i, i, i, i, i, p3, p3, p3, p3, vp, vp, vp]
         lib.vats_attn_decode.restype = i
@@ -87,6 +118,8 @@ def load() -> ctypes.CDLL:
                                                   i, f, vp]
         lib.vats_attn_last_launch_count.restype = i
         lib.vats_attn_last_launch_count.argtypes = []
+        lib.vats_attn_last_kernel.restype = i
+        lib.vats_attn_last_kernel.argtypes = []
         lib.vats_attn_debug_mask.restype = i
         lib.vats_attn_debug_mask.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp]
         lib.vats_attn_debug_tile_range.restype = i
@@ -116,21 +149,38 @@ def last_launch_count() -> int:
     return load().vats_attn_last_launch_count()
 
 
+LAUNCHED = {0: "none", 1: "prefill_tc", 2: "prefill_tc_ldg", 3: "prefill_short", 4: "prefill_simt", 5: "decode_mma",
+            6: "decode_split", 7: "prefill_prepare", 8: "decode_prepare", 9: "prefill_mid", 10: "backward"}
+
+
+def last_kernel() -> str:
+    """Name of the kernel the last successful compute call of this thread ended in (include/vats_attn.h)."""
+    return LAUNCHED.get(load().vats_attn_last_kernel(), "unknown")
+
+
 def prefill(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int],
             N: int, Tq: int, Tk: int, H: int, G: int, hd: int,
             q_strides: Sequence[int], k_strides: Sequence[int], v_strides: Sequence[int], o_strides: Sequence[int],
-            scale: float, causal: bool, left: int, right: int, stream: int, kernel: int = KERNEL_AUTO) -> None:
+            scale: float, causal: bool, left: int, right: int, stream: int, kernel: int = KERNEL_AUTO,
+            workspace_ptr: Optional[int] = None, workspace_bytes: int = 0) -> None:
     lib = load()
-    _check(lib.vats_attn_prefill_ex(
+    _check(lib.vats_attn_prefill_ws(
         q_ptr, k_ptr, v_ptr, o_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd,
-        _i64x3(*q_strides), _i64x3(*k_strides), _i64x3(*v_strides), _i64x3(*o_strides),
-        float(scale), int(bool(causal)), int(left), int(right), int(kernel), stream))
+        _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
+        float(scale), int(bool(causal)), int(left), int(right), int(kernel), workspace_ptr, workspace_bytes, stream))
+
+
+def prefill_workspace_bytes(N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides,
+                            q_ptr: int, k_ptr: int, v_ptr: int) -> int:
+    """Scratch the tensor-core kernel wants for tensors TMA cannot address (0 = none); see include/vats_attn.h."""
+    return int(load().vats_attn_prefill_workspace_bytes(N, Tq, Tk, H, G, hd, _s3(q_strides), _s3(k_strides),
+                                                        _s3(v_strides), q_ptr, k_ptr, v_ptr))
 
 
 def prefill_plan(N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides, o_strides,
                  q_ptr: int, k_ptr: int, v_ptr: int) -> int:
-    return load().vats_attn_prefill_plan(N, Tq, Tk, H, G, hd, _i64x3(*q_strides), _i64x3(*k_strides),
-                                         _i64x3(*v_strides), _i64x3(*o_strides), q_ptr, k_ptr, v_ptr)
+    return load().vats_attn_prefill_plan(N, Tq, Tk, H, G, hd, _s3(q_strides), _s3(k_strides),
+                                         _s3(v_strides), _s3(o_strides), q_ptr, k_ptr, v_ptr)
 
 
 def decode_workspace_bytes(B: int, H: int, G: int, hd: int, S_max: int, left: int) -> int:
@@ -144,7 +194,7 @@ def decode(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, seq_lens_ptr: int, B:
     lib = load()
     _check(lib.vats_attn_decode(
         q_ptr, k_ptr, v_ptr, o_ptr, seq_lens_ptr, B, H, G, hd, S_max,
-        _i64x2(*q_strides), _i64x3(*k_strides), _i64x3(*v_strides), _i64x2(*o_strides),
+        _s2(q_strides), _s3(k_strides), _s3(v_strides), _s2(o_strides),
         float(scale), int(left), workspace_ptr, workspace_bytes, stream))
 
 
@@ -154,8 +204,8 @@ def decode_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, q
                    v_strides, qk_norm: bool, eps: float, stream: int) -> None:
     _check(load().vats_attn_decode_prepare(
         q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_cache_ptr, v_cache_ptr, seq_lens_ptr, cos_ptr,
-        sin_ptr, B, H, G, hd, S_max, _i64x2(*qin_strides), _i64x2(*kin_strides), _i64x2(*vin_strides),
-        _i64x2(*qout_strides), _i64x3(*k_strides), _i64x3(*v_strides), int(bool(qk_norm)), float(eps), stream))
+        sin_ptr, B, H, G, hd, S_max, _s2(qin_strides), _s2(kin_strides), _s2(vin_strides),
+        _s2(qout_strides), _s3(k_strides), _s3(v_strides), int(bool(qk_norm)), float(eps), stream))
 
 
 def prefill_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, q_out_ptr: int, k_out_ptr: int,
@@ -164,8 +214,8 @@ def prefill_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, 
                     qk_norm: bool, eps: float, stream: int) -> None:
     _check(load().vats_attn_prefill_prepare(
         q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_out_ptr, v_out_ptr, cos_ptr, sin_ptr, N, T, H, G,
-        hd, pos0, _i64x3(*qin_strides), _i64x3(*kin_strides), _i64x3(*vin_strides), _i64x3(*qout_strides),
-        _i64x3(*kout_strides), _i64x3(*vout_strides), int(bool(qk_norm)), float(eps), stream))
+        hd, pos0, _s3(qin_strides), _s3(kin_strides), _s3(vin_strides), _s3(qout_strides),
+        _s3(kout_strides), _s3(vout_strides), int(bool(qk_norm)), float(eps), stream))
 
 
 def debug_mask(out_ptr: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int], N: int, Tq: int, Tk: int,

@@ -1,7 +1,8 @@
 // decode_mma.cuh — KV-cache single-query GQA + sliding-window attention, TMA-fed and HBM-bound.
 //
 // Same contract as decode.cuh (reference src/optimized_attention.py:508-516 + 709-714, cache KVCache :169-287); this
-// is the fast path for TMA-addressable caches (head_dim % 16 == 0, 16-byte aligned strides).
+// is the fast path for TMA-addressable caches (even head_dim <= 128, 16-byte aligned base and strides — the drop-in
+// KVCache rounds the head stride up to 8 elements, so hd 60 qualifies).
 //
 // The kernel is a byte pump: decode is 4 flop/byte, so everything is organised around keeping 128 KB of K/V in
 // flight per SM, spending almost no issue slots per byte, and never stalling the consumers at an item boundary.
@@ -91,7 +92,8 @@ __device__ __forceinline__ DmItem dm_decode_item(const DecodeMmaParams& P, int i
   return it;
 }
 
-// HD: head dim (multiple of 16, <= 128).  Shared memory: [stages][K halves | V halves][32 keys][128 B] + merge scratch.
+// HD: tile width = head dim rounded up to 16 / 32 / 64 / 128 (d.hd <= HD is the real head dim: TMA zero-fills the
+// columns past it, e.g. hd 60 in a cache whose head stride is 64).  Shared memory: [stages][K halves | V halves][32 keys][128 B] + merge scratch.
 template <int HD, int NCW, int SK>
 __global__ void __launch_bounds__((2 * NCW + 1) * 32, 1)
 decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap tmap_k,
@@ -175,7 +177,7 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
             const float invL = L > 0.f ? 1.f / L : 0.f;
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
-              if (c * 32 + lane < HD)
+              if (c * 32 + lane < d.hd)
                 d.o[it.b * d.os_b + (long long)hq * d.os_h + c * 32 + lane] = __float2bfloat16(acc[c] * invL);
           } else {
             const long long slot = (long long)(it.b * d.H + hq) * d.num_splits + it.split;
@@ -246,7 +248,7 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
             const float invL = Lh[h] > 0.f ? 1.f / Lh[h] : 0.f;
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
-              if (h < nh && c * 32 + lane < HD)
+              if (h < nh && c * 32 + lane < d.hd)
                 d.o[it.b * d.os_b + (long long)(h0 + h) * d.os_h + c * 32 + lane] = __float2bfloat16(accm[h][c] * invL);
           }
           if (lane == 0) P.counters[unit] = 0;  // leave the workspace ready for the next call
@@ -312,8 +314,12 @@ decode_mma_kernel(const DecodeMmaParams P, const __grid_constant__ CUtensorMap t
         qa[ks][0] = 0u;
         qa[ks][1] = 0u;
         if (quad < nh && it.nst > 0) {
-          qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + qlane * 2);
-          qa[ks][1] = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + qlane * 2);
+          // head dims below HD (60 in a 64-wide tile): the columns past hd are zero-filled by TMA in K / V and must
+          // be zero (and unread) in Q
+          if (HD == d.hd || ks * 16 + qlane * 2 < d.hd)
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + qlane * 2);
+          if (HD == d.hd || ks * 16 + 8 + qlane * 2 < d.hd)
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + qlane * 2);
         }
       }
     }

@@ -28,6 +28,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
+thread_local int g_last_kernel = 0;   // VATS_LAUNCHED_* of the last successful launch on this thread
 unsigned long long* g_trace = nullptr;  // debug timeline buffer (device memory), see vats_attn_debug_set_trace
 int g_trace_cap = 0;
 
@@ -46,11 +47,29 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ---- device gate: sm_100 only
+constexpr int kMaxDevices = 64;
+thread_local int g_dev = 0;   // current device of the calling thread, refreshed by check_device() at every entry point
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember what was set per
+// device, not per process — one thread may launch on cuda:0 and then on cuda:1.
+struct SmemAttrCache {
+  size_t set[kMaxDevices] = {};
+};
+template <typename Kernel>
+cudaError_t ensure_dyn_smem(Kernel kernel, size_t smem, SmemAttrCache& cache) {
+  const bool tracked = g_dev >= 0 && g_dev < kMaxDevices;
+  if (tracked && smem <= cache.set[g_dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && tracked) cache.set[g_dev] = smem;
+  return e;
+}
+
 int check_device() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess)
     return fail(VATS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  g_dev = dev;
   static thread_local int cached_dev = -1;
   static thread_local int cached_ok = 0;
   if (cached_dev == dev) return cached_ok ? VATS_OK : fail(VATS_ERR_UNSUPPORTED, "device %d is not sm_100", dev);
@@ -142,6 +161,8 @@ struct PrefillArgs {
   const int64_t *qs, *ks, *vs, *os;
   float scale;
   int causal, left, right;
+  void* ws = nullptr;       // caller-owned scratch (vats_attn_prefill_workspace_bytes), may be NULL
+  size_t ws_bytes = 0;
 };
 
 int validate_prefill(const PrefillArgs& A) {
@@ -220,6 +241,7 @@ int launch_simt(const PrefillArgs& A, cudaStream_t st) {
 #undef VATS_SIMT_CASE
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_PREFILL_SIMT;
   return VATS_OK;
 }
 
@@ -329,12 +351,8 @@ int launch_short(const PrefillArgs& A, cudaStream_t st) {
   P.trace_cap = g_trace_cap;
 #define VATS_SHORT_LAUNCH(K, B)                                                                                    \
   {                                                                                                                \
-    static thread_local size_t set = 0;                                                                            \
-    if (smem > set) {                                                                                              \
-      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_short_kernel<K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                   \
-      set = smem;                                                                                                  \
-    }                                                                                                              \
+    static thread_local SmemAttrCache set;                                                                         \
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_short_kernel<K, B>, smem, set));                                        \
     vats::prefill_short_kernel<K, B><<<(unsigned)grid, threads, smem, st>>>(P);                                    \
   }
 #define VATS_SHORT_CASE(K)               \
@@ -349,14 +367,28 @@ int launch_short(const PrefillArgs& A, cudaStream_t st) {
 #undef VATS_SHORT_LAUNCH
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_PREFILL_SHORT;
   return VATS_OK;
 }
 
 int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st);
 
-// q / k / v with rows TMA cannot address: one streaming repack into a stream-ordered scratch buffer (head stride
-// rounded up to 8 elements), then the TMA-fed kernel on the copies.  Returns -1 if the scratch cannot be had
-// (the caller then uses the kernel's own cp.async staging variant).
+// q / k / v with rows TMA cannot address: one streaming repack into the CALLER's scratch buffer (head stride rounded
+// up to 8 elements), then the TMA-fed kernel on the copies.  Returns -1 if no (or too small a) scratch was given —
+// the caller then uses the kernel's own cp.async staging variant.  The library allocates nothing.
+size_t tc_repack_offsets(const PrefillArgs& A, const TcPlan& pl, size_t off[4]) {
+  const int hd_pad = (A.hd + 7) / 8 * 8;
+  const int Ts[3] = {A.Tq, A.Tk, A.Tk};
+  const int heads[3] = {A.H, A.G, A.G};
+  const LoadMode modes[3] = {pl.q, pl.k, pl.v};
+  off[0] = 0;
+  for (int i = 0; i < 3; ++i) {
+    const size_t bytes = modes[i] == LoadMode::kLdg ? (size_t)A.N * Ts[i] * heads[i] * hd_pad * 2 : 0;
+    off[i + 1] = off[i] + ((bytes + 255) & ~(size_t)255);
+  }
+  return off[3];
+}
+
 int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   static int enabled = -1;
   if (enabled < 0) {
@@ -370,37 +402,18 @@ int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) 
   const int Ts[3] = {A.Tq, A.Tk, A.Tk};
   const int heads[3] = {A.H, A.G, A.G};
   const LoadMode modes[3] = {pl.q, pl.k, pl.v};
-  size_t off[4] = {0, 0, 0, 0};
-  for (int i = 0; i < 3; ++i) {
-    const size_t bytes = modes[i] == LoadMode::kLdg ? (size_t)A.N * Ts[i] * heads[i] * hd_pad * 2 : 0;
-    off[i + 1] = off[i] + ((bytes + 255) & ~(size_t)255);
-  }
-  {
-    // keep freed scratch in the device's stream-ordered pool (the default threshold hands it back to the driver at
-    // every synchronisation, which makes each call pay for a fresh multi-hundred-MB allocation)
-    static thread_local int pool_dev = -1;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev != pool_dev) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      (void)cudaGetLastError();
-      pool_dev = dev;
-    }
-  }
-  void* ws = nullptr;
-  if (cudaMallocAsync(&ws, off[3], st) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return -1;
-  }
+  size_t off[4];
+  const size_t need = tc_repack_offsets(A, pl, off);
+  if (!A.ws || A.ws_bytes < need || (reinterpret_cast<uintptr_t>(A.ws) & 15u) != 0) return -1;
+  void* ws = A.ws;
   vats::RepackParams R;
   std::memset(&R, 0, sizeof(R));
   R.hd2 = A.hd / 2;
   R.hd_pad = hd_pad;
   int64_t new_str[3][3];
   PrefillArgs B = A;
+  B.ws = nullptr;
+  B.ws_bytes = 0;
   long long max_rows = 0;
   int nrep = 0;
   for (int i = 0; i < 3; ++i) {
@@ -431,7 +444,6 @@ int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) 
     TcPlan pl2{LoadMode::kTma, LoadMode::kTma, LoadMode::kTma};
     rc = launch_tc(B, pl2, st);
   }
-  cudaFreeAsync(ws, st);
   if (rc == VATS_OK) g_launches += 1;
   return rc;
 }
@@ -527,20 +539,18 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.trace_cap = g_trace_cap;
   int grid = sm_count();
   if (grid > P.num_work) grid = P.num_work;
-  static thread_local size_t smem_set[2] = {0, 0};
-  if (smem > smem_set[any_ldg ? 1 : 0]) {
-    if (any_ldg)
-      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      CUDA_TRY(cudaFuncSetAttribute(vats::prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[any_ldg ? 1 : 0] = smem;
-  }
+  static thread_local SmemAttrCache smem_set[2];
+  if (any_ldg)
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_tc_kernel<true>, smem, smem_set[1]));
+  else
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_tc_kernel<false>, smem, smem_set[0]));
   if (any_ldg)
     vats::prefill_tc_kernel<true><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
   else
     vats::prefill_tc_kernel<false><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = any_ldg ? VATS_LAUNCHED_PREFILL_TC_LDG : VATS_LAUNCHED_PREFILL_TC;
   return VATS_OK;
 }
 
@@ -655,10 +665,21 @@ void decode_mma_plan(int B, int G, int hpg, int S_max, int left, int* hpg_tile, 
   *splits = (int)((window + ch - 1) / ch);
 }
 
+// tile width of the mma decode kernel for a head dim (template parameter HD)
+int decode_mma_tile_hd(int hd) { return hd <= 16 ? 16 : (hd <= 32 ? 32 : (hd <= 64 ? 64 : 128)); }
+
+// bytes of the split counters at the head of the decode workspace (one int per (sequence, KV group, head batch))
+size_t decode_counter_bytes(int B, int H, int G) {
+  const int hpg = H / G;
+  const int hb = (hpg + vats::kDmMaxHeads - 1) / vats::kDmMaxHeads;
+  return ((size_t)B * G * hb * sizeof(int) + 255) / 256 * 256;
+}
+
 size_t decode_mma_ws_bytes(int B, int H, int G, int hd, int S_max, int left) {
+  hd = decode_mma_tile_hd(hd);
   int tile, hb, chunk, ns;
   decode_mma_plan(B, G, H / G, S_max, left, &tile, &hb, &chunk, &ns);
-  const size_t counters = ((size_t)B * G * hb * sizeof(int) + 255) / 256 * 256;
+  const size_t counters = decode_counter_bytes(B, H, G);
   return counters + (ns > 1 ? (size_t)B * H * ns * ((size_t)hd + 2) * sizeof(float) : 0);
 }
 
@@ -681,12 +702,8 @@ int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUt
   if (stages < NCW) return fail(VATS_ERR_UNSUPPORTED, "decode: shared memory too small for the stage ring");
   const size_t smem = vats::decode_mma_smem_bytes<HD, NCW, SK>(stages);
   P.stages = stages;
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(vats::decode_mma_kernel<HD, NCW, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    smem_set = smem;
-  }
+  static thread_local SmemAttrCache smem_set;
+  CUDA_TRY(ensure_dyn_smem(vats::decode_mma_kernel<HD, NCW, SK>, smem, smem_set));
   int grid = sm_count();
   if (grid > P.num_items) grid = P.num_items;
   vats::decode_mma_kernel<HD, NCW, SK><<<grid, (2 * NCW + 1) * 32, smem, st>>>(P, mk, mv);
@@ -722,6 +739,7 @@ void vats_attn_debug_set_trace(void* dev_buf, int capacity) {
 }
 const char* vats_attn_last_error(void) { return g_err; }
 int vats_attn_last_launch_count(void) { return g_launches; }
+int vats_attn_last_kernel(void) { return g_last_kernel; }
 
 int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o, const uint8_t* q_valid,
                          const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
@@ -731,6 +749,33 @@ int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o, c
   PrefillArgs A{q, k, v, o, q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
                 scale, causal, left, right};
   return prefill_impl(A, kernel, stream);
+}
+
+int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o, const uint8_t* q_valid,
+                         const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
+                         const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                         const int64_t o_strides[3], float scale, int causal, int left, int right, int kernel,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  PrefillArgs A{q, k, v, o, q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
+                scale, causal, left, right};
+  A.ws = workspace;
+  A.ws_bytes = workspace ? workspace_bytes : 0;
+  return prefill_impl(A, kernel, stream);
+}
+
+size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, int hd, const int64_t q_strides[3],
+                                         const int64_t k_strides[3], const int64_t v_strides[3], const void* q,
+                                         const void* k, const void* v) {
+  if (N <= 0 || Tq <= 0 || Tk <= 0 || H <= 0 || G <= 0 || hd <= 0 || H % G != 0 || !q_strides || !k_strides ||
+      !v_strides)
+    return 0;
+  PrefillArgs A{q, k, v, nullptr, nullptr, nullptr, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, q_strides,
+                1.f, 0, -1, -1};
+  TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
+  if (choose_kernel(A, &pl) != VATS_KERNEL_TCGEN05) return 0;
+  if (pl.q != LoadMode::kLdg && pl.k != LoadMode::kLdg && pl.v != LoadMode::kLdg) return 0;
+  size_t off[4];
+  return tc_repack_offsets(A, pl, off);
 }
 
 int vats_attn_prefill(const void* q, const void* k, const void* v, void* o, const uint8_t* q_valid,
@@ -796,6 +841,7 @@ int vats_attn_prefill_prepare(const void* q_in, const void* k_in, const void* v_
   vats::prefill_prepare_kernel<<<(unsigned)blocks, vats::kPrepareWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_PREFILL_PREPARE;
   return VATS_OK;
 }
 
@@ -843,16 +889,19 @@ int vats_attn_decode_prepare(const void* q_in, const void* k_in, const void* v_i
   vats::decode_prepare_kernel<<<(unsigned)blocks, vats::kPrepareWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_DECODE_PREPARE;
   return VATS_OK;
 }
 
 size_t vats_attn_decode_workspace_bytes(int B, int H, int G, int hd, int S_max, int left) {
-  (void)G;
   if (B <= 0 || H <= 0 || hd <= 0 || S_max <= 0) return 0;
   if (G <= 0 || H % G != 0) return 0;
+  // layout: [split counters of the mma kernel | fp32 partials of whichever kernel runs].  The CUDA-core kernel's
+  // partials start behind the counter region too, so it can never leave a non-zero counter behind.
   int chunk, splits;
   decode_chunk_and_splits(S_max, left, &chunk, &splits);
-  const size_t simt = splits <= 1 ? 16 : (size_t)B * H * splits * ((size_t)hd + 2) * sizeof(float);
+  const size_t simt = decode_counter_bytes(B, H, G) +
+                      (splits <= 1 ? 16 : (size_t)B * H * splits * ((size_t)hd + 2) * sizeof(float));
   const size_t mma = decode_mma_ws_bytes(B, H, G, hd, S_max, left);
   return simt > mma ? simt : mma;
 }
@@ -899,13 +948,13 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
     const size_t need = vats_attn_decode_workspace_bytes(B, H, G, hd, S_max, left);
     if (!workspace || workspace_bytes < need)
       return fail(VATS_ERR_WORKSPACE, "decode workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-    p.ws_acc = reinterpret_cast<float*>(workspace);
+    p.ws_acc = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + decode_counter_bytes(B, H, G));
     p.ws_ml = p.ws_acc + (size_t)B * H * p.num_splits * hd;
   }
 
   // ---- fast path: TMA-addressable cache (16-byte aligned base / strides, head_dim multiple of 16 up to 128)
   {
-    const bool tma_ok = (hd == 16 || hd == 32 || hd == 64 || hd == 128) && S_max > 0 &&
+    const bool tma_ok = hd <= 128 && S_max > 0 &&
                         (reinterpret_cast<uintptr_t>(k_cache) & 15u) == 0 &&
                         (reinterpret_cast<uintptr_t>(v_cache) & 15u) == 0 && k_strides[0] % 8 == 0 &&
                         k_strides[1] % 8 == 0 && k_strides[2] % 8 == 0 && v_strides[0] % 8 == 0 &&
@@ -920,17 +969,17 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
       const size_t need = decode_mma_ws_bytes(B, H, G, hd, S_max, left);
       if (!workspace || workspace_bytes < need)
         return fail(VATS_ERR_WORKSPACE, "decode workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-      const size_t counters = ((size_t)B * G * P.d.head_batches * sizeof(int) + 255) / 256 * 256;
+      const size_t counters = decode_counter_bytes(B, H, G);
       P.counters = reinterpret_cast<int*>(workspace);
       P.d.ws_acc = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + counters);
-      P.d.ws_ml = P.d.ws_acc + (size_t)B * H * P.d.num_splits * hd;
+      P.d.ws_ml = P.d.ws_acc + (size_t)B * H * P.d.num_splits * decode_mma_tile_hd(hd);
       const long long items = (long long)B * G * P.d.head_batches * P.d.num_splits;
       if (items > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "decode: too many work items");
       P.num_items = (int)items;
       CUtensorMap mk, mv;
       if ((rc = encode_map(&mk, k_cache, B, S_max, G, hd, k_strides, decode_mma_stage_keys())) != VATS_OK) return rc;
       if ((rc = encode_map(&mv, v_cache, B, S_max, G, hd, v_strides, decode_mma_stage_keys())) != VATS_OK) return rc;
-      switch (hd) {
+      switch (decode_mma_tile_hd(hd)) {
         case 16: rc = launch_decode_mma_ncw<16>(P, mk, mv, st); break;
         case 32: rc = launch_decode_mma_ncw<32>(P, mk, mv, st); break;
         case 64: rc = launch_decode_mma_ncw<64>(P, mk, mv, st); break;
@@ -938,6 +987,7 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
       }
       if (rc != VATS_OK) return rc;
       g_launches = 1;
+      g_last_kernel = VATS_LAUNCHED_DECODE_MMA;
       return VATS_OK;
     }
   }
@@ -994,6 +1044,7 @@ int vats_attn_decode(const void* q, const void* k_cache, const void* v_cache, vo
   if (rc != VATS_OK) return rc;
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_DECODE_SPLIT;
   if (p.num_splits > 1) {
     vats::decode_combine_kernel<<<B * H, 128, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());

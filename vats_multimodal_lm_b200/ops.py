@@ -12,13 +12,14 @@ device in bf16; anything else raises — there is deliberately no eager / CPU pa
 """
 from __future__ import annotations
 
+import collections
 from typing import List, Optional
 
 import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -76,12 +77,25 @@ def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: 
         return o
     with torch.cuda.device(q.device):
         stream = torch.cuda.current_stream().cuda_stream
-        _ffi.prefill(q.data_ptr(), k.data_ptr() if k.numel() else None, v.data_ptr() if v.numel() else None,
-                     o.data_ptr(), qv.data_ptr() if qv is not None else None,
+        qs, ks, vs = q.stride()[:3], k.stride()[:3], v.stride()[:3]
+        kp, vp = (k.data_ptr(), v.data_ptr()) if k.numel() else (None, None)
+        # rows TMA cannot address (dense hd 60 / 66): the kernel repacks them into scratch that WE own (the library
+        # allocates nothing); tensors in the modules' padded layout need none
+        ws, ws_bytes = None, 0
+        if kp is not None and kernel != KERNEL_SIMT and (hd % 8 != 0 or not _tma_strides(qs, ks, vs) or
+                                                         (q.data_ptr() | kp | vp) & 15):
+            ws_bytes = _ffi.prefill_workspace_bytes(N, Tq, Tk, H, G, hd, qs, ks, vs, q.data_ptr(), kp, vp)
+            if ws_bytes:
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        _ffi.prefill(q.data_ptr(), kp, vp, o.data_ptr(), qv.data_ptr() if qv is not None else None,
                      kv.data_ptr() if kv is not None else None,
-                     N, Tq, Tk, H, G, hd, q.stride()[:3], k.stride()[:3], v.stride()[:3], o.stride()[:3],
-                     scale, causal, left, right, stream, kernel)
+                     N, Tq, Tk, H, G, hd, qs, ks, vs, o.stride()[:3],
+                     scale, causal, left, right, stream, kernel, ws.data_ptr() if ws is not None else None, ws_bytes)
     return o
+
+
+def _tma_strides(*stride_sets) -> bool:
+    return all(s % 8 == 0 for ss in stride_sets for s in ss)
 
 
 @gqa_swa_prefill.register_fake
@@ -89,22 +103,36 @@ def _(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
     return q.new_empty(q.shape, dtype=torch.bfloat16)
 
 
-_DECODE_WS = {}
+# Split-K scratch of the decode kernels.  The C-ABI wants its head (the split counters) ZERO on entry and leaves it
+# zero on exit, so in eager mode one zero-filled buffer per (device, stream, geometry) is created once and reused by
+# the stream-ordered calls that share it — no memset per step.  Rules that keep that invariant sound:
+#   * while a CUDA graph is being captured the cache is neither used nor touched: the call gets a fresh torch.zeros
+#     from the graph's own pool (the memset becomes a graph node, the buffer lives as long as the graph);
+#   * eviction is LRU, one entry at a time (never a wholesale clear);
+#   * a failed decode call drops its entry (the counters may be dirty); `reset_decode_workspaces()` drops all of them,
+#     e.g. after a device-side fault.
+_DECODE_WS: "collections.OrderedDict" = collections.OrderedDict()
+_DECODE_WS_MAX = 64
 
 
-def _decode_workspace(device, stream: int, B: int, H: int, G: int, hd: int, S_max: int, left: int) -> torch.Tensor:
-    """Split-K scratch for the decode kernels.  The C-ABI wants it zero-filled before its first use (the kernel's
-    split counters live there and are left at zero on return), so it is created once per (device, stream, geometry)
-    with torch.zeros and reused; calls sharing one workspace are ordered by their stream."""
+def reset_decode_workspaces() -> None:
+    """Forget every cached decode workspace (they are re-created zero-filled on next use)."""
+    _DECODE_WS.clear()
+
+
+def _decode_workspace(device, stream: int, B: int, H: int, G: int, hd: int, S_max: int, left: int):
+    nbytes = max(_ffi.decode_workspace_bytes(B, H, G, hd, S_max, left), 16)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros((nbytes,), dtype=torch.uint8, device=device), None
     key = (device.index, stream, B, H, G, hd, S_max, left)
     ws = _DECODE_WS.get(key)
     if ws is None:
-        if len(_DECODE_WS) > 64:
-            _DECODE_WS.clear()
-        nbytes = max(_ffi.decode_workspace_bytes(B, H, G, hd, S_max, left), 16)
-        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
-        _DECODE_WS[key] = ws
-    return ws
+        while len(_DECODE_WS) >= _DECODE_WS_MAX:
+            _DECODE_WS.popitem(last=False)
+        ws = _DECODE_WS[key] = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+    else:
+        _DECODE_WS.move_to_end(key)
+    return ws, key
 
 
 @torch.library.custom_op("vats::gqa_swa_decode", mutates_args=(), device_types="cuda")
@@ -133,10 +161,14 @@ def gqa_swa_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor
         return o
     with torch.cuda.device(q.device):
         stream = torch.cuda.current_stream().cuda_stream
-        ws = _decode_workspace(q.device, stream, B, H, G, hd, S_max, left)
-        _ffi.decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), o.data_ptr(), seq_lens.data_ptr(),
-                    B, H, G, hd, S_max, q.stride()[:2], k_cache.stride()[:3], v_cache.stride()[:3], o.stride()[:2],
-                    scale, left, ws.data_ptr(), ws.numel(), stream)
+        ws, key = _decode_workspace(q.device, stream, B, H, G, hd, S_max, left)
+        try:
+            _ffi.decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), o.data_ptr(), seq_lens.data_ptr(),
+                        B, H, G, hd, S_max, q.stride()[:2], k_cache.stride()[:3], v_cache.stride()[:3], o.stride()[:2],
+                        scale, left, ws.data_ptr(), ws.numel(), stream)
+        except _ffi.VatsAttnError:
+            _DECODE_WS.pop(key, None)   # its counters may be dirty: never reuse it
+            raise
     return o
 
 
