@@ -58,6 +58,7 @@ extern "C" {
 #define VATS_KERNEL_AUTO 0    /* shape-based choice (what vats_attn_prefill uses) */
 #define VATS_KERNEL_TCGEN05 1 /* TMA + tcgen05/TMEM tile kernel; error if the geometry is not TMA-legal */
 #define VATS_KERNEL_SIMT 2    /* CUDA-core warp kernel for tiny / irregular sequences */
+#define VATS_KERNEL_MID 3     /* tcgen05 kernel for <= 256 keys: K/V of a KV group resident in shared memory */
 
 /*
  * Prefill / encoder attention:  O[n,i,h,:] = softmax_j( scale * <Q[n,i,h,:], K[n,j,h/(H/G),:]> | allowed ) . V[n,j,h/(H/G),:]
@@ -104,7 +105,7 @@ size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, in
                                          const int64_t v_strides[3],
                                          const void* q, const void* k, const void* v);
 
-/* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / VATS_KERNEL_SIMT). Host only. */
+/* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / _SIMT / _MID). Host only. */
 int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
                            const int64_t q_strides[3], const int64_t k_strides[3],
                            const int64_t v_strides[3], const int64_t o_strides[3],

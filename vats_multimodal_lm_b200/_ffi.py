@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("VATS_ATTN_LIB") or os.path.join(_HERE, "csrc", "libva
 KERNEL_AUTO = 0
 KERNEL_TCGEN05 = 1
 KERNEL_SIMT = 2
+KERNEL_MID = 3
 
 # every symbol include/vats_attn.h declares (tests check that the library exports exactly these)
 EXPORTED_SYMBOLS = (

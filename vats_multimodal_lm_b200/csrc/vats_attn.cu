@@ -21,6 +21,7 @@
 #include "prefill_simt.cuh"
 #include "prefill_tc.cuh"
 #include "prefill_short.cuh"
+#include "prefill_mid.cuh"
 #include "decode_prepare.cuh"
 #include "repack.cuh"
 
@@ -119,7 +120,7 @@ LoadMode plan_load(const void* ptr, int hd, const int64_t s[3]) {
 }
 
 int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int hd, const int64_t s[3],
-               int box_rows = 128) {
+               int box_rows = 128, int box_heads = 1) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)heads, (cuuint64_t)T, (cuuint64_t)N};
@@ -128,7 +129,7 @@ int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int h
   if (heads == 1 || strides[0] == 0) strides[0] = (cuuint64_t)((hd + 7) / 8 * 8) * 2;
   if (T == 1 || strides[1] == 0) strides[1] = strides[0] * (cuuint64_t)heads;
   if (N == 1 || strides[2] == 0) strides[2] = strides[1] * (cuuint64_t)T;
-  const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_heads, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -554,6 +555,106 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   return VATS_OK;
 }
 
+// Sequences of at most 256 keys: K / V of a (sequence, KV group) resident in shared memory for all of the group's heads
+// and query blocks, single-pass softmax, two tile slots (prefill_mid.cuh).  Returns -1 when the geometry does not
+// qualify (the caller then uses the 128 x 128 tile kernel).
+bool mid_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("VATS_PREFILL_MID");  // tuning knob: 0 = always the 128 x 128 tile kernel
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return enabled != 0;
+}
+
+bool mid_legal(const PrefillArgs& A, const TcPlan& pl) {
+  if (A.Tk < 1 || A.Tk > 256 || A.hd > 128 || A.hd % 2 != 0) return false;
+  if (pl.q == LoadMode::kNone || pl.k == LoadMode::kNone || pl.v == LoadMode::kNone) return false;
+  if (plan_load(A.o, A.hd, A.os) == LoadMode::kNone) return false;
+  if ((long long)A.N * A.G > 0x3fffffffLL) return false;
+  return true;
+}
+
+int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
+  if (!mid_legal(A, pl)) return -1;
+  vats::MidParams P;
+  std::memset(&P, 0, sizeof(P));
+  fill_common(P.a, A);
+  const int hpg = P.a.hpg;
+  P.hd_pad = (A.hd + 15) / 16 * 16;
+  P.regions = (P.hd_pad + 63) / 64;
+  P.n_pad = (A.Tk + 15) / 16 * 16;
+  P.o_off = (P.n_pad / 2 + 15) / 16 * 16;
+  // pack the group's heads into the tile rows when their count is a power of two (TMA box {64, pack, 128 / pack})
+  int pack = 1;
+  if ((hpg & (hpg - 1)) == 0) pack = hpg > 32 ? 32 : hpg;
+  P.pack = pack;
+  P.pack_shift = 0;
+  while ((1 << P.pack_shift) < pack) ++P.pack_shift;
+  P.tok_per_tile = 128 >> P.pack_shift;
+  P.q_tiles = (A.Tq + P.tok_per_tile - 1) / P.tok_per_tile;
+  P.head_sets = hpg / pack;
+  const long long tpi = (long long)P.q_tiles * P.head_sets;
+  if (tpi > 0x3fffffLL) return -1;
+  P.tiles_per_item = (int)tpi;
+  P.num_items = A.N * A.G;
+  const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  {
+    auto al8 = [&](const void* ptr, const int64_t* st3) {
+      return (reinterpret_cast<uintptr_t>(ptr) & 7u) == 0 && st3[0] % 4 == 0 && st3[1] % 4 == 0 && st3[2] % 4 == 0;
+    };
+    P.ldg_vec = (A.hd % 4 == 0 && al8(A.q, A.qs) && al8(A.k, A.ks) && al8(A.v, A.vs)) ? 2 : 1;
+  }
+  P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;
+  P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
+  const long long q_bytes = 2LL * P.regions * vats::kMidQRegionBytes;
+  const long long kv_stage = 2LL * P.regions * P.n_pad * 128;
+  const long long budget = 227LL * 1024 - 1024 - (long long)sizeof(vats::MidBarriers) - q_bytes - 8 * vats::kTcOStageBytes;
+  long long nkv = budget / kv_stage;
+  if (nkv < 1) return -1;
+  if (nkv > vats::kMidMaxKv) nkv = vats::kMidMaxKv;
+  {
+    static int nkv_env = -1;
+    if (nkv_env < 0) {
+      const char* e = getenv("VATS_PREFILL_MID_STAGES");  // tuning knob: K / V ring depth
+      nkv_env = e ? atoi(e) : 0;
+    }
+    if (nkv_env >= 1 && nkv_env < nkv) nkv = nkv_env;
+  }
+  P.nkv = (int)nkv;
+  const size_t smem = vats::mid_smem_bytes(P.regions, P.n_pad, P.nkv);
+  vats::tc_find_divisor((unsigned)A.G, P.div_g);
+  vats::tc_find_divisor((unsigned)P.q_tiles, P.div_qt);
+
+  CUtensorMap mq, mk, mv, mo;
+  std::memset(&mq, 0, sizeof(mq));
+  std::memset(&mk, 0, sizeof(mk));
+  std::memset(&mv, 0, sizeof(mv));
+  std::memset(&mo, 0, sizeof(mo));
+  int rc;
+  if (!any_ldg) {
+    if ((rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs, P.tok_per_tile, pack)) != VATS_OK) return rc;
+    if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks, P.n_pad)) != VATS_OK) return rc;
+    if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs, P.n_pad)) != VATS_OK) return rc;
+  }
+  if (P.o_stage == 1 && (rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32 >> P.pack_shift, pack)) != VATS_OK)
+    return rc;
+  int grid = sm_count();
+  if (grid > P.num_items) grid = P.num_items;
+  static thread_local SmemAttrCache smem_set[2];
+  if (any_ldg) {
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_mid_kernel<true>, smem, smem_set[1]));
+    vats::prefill_mid_kernel<true><<<(unsigned)grid, vats::kMidThreads, smem, st>>>(P, mq, mk, mv, mo);
+  } else {
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_mid_kernel<false>, smem, smem_set[0]));
+    vats::prefill_mid_kernel<false><<<(unsigned)grid, vats::kMidThreads, smem, st>>>(P, mq, mk, mv, mo);
+  }
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_PREFILL_MID;
+  return VATS_OK;
+}
+
 int choose_kernel(const PrefillArgs& A, TcPlan* pl) {
   const bool legal = tc_legal(A, pl);
   if (!legal) return VATS_KERNEL_SIMT;
@@ -565,6 +666,9 @@ int choose_kernel(const PrefillArgs& A, TcPlan* pl) {
   // tokens) also run faster on 128-row tiles (0.154 ms) than on the short-sequence kernel's token chunks (0.229 ms;
   // generic warp kernel 0.379 ms): the cut is at two query blocks.
   if (A.Tk < 32 && A.Tq < 256) return VATS_KERNEL_SIMT;
+  // At most 256 keys: the whole K / V of a (sequence, KV group) is one tile — the resident-K/V kernel (ViT spatial
+  // passes, text encoders, cross-attention contexts, short prompts).
+  if (A.Tk <= 256 && mid_enabled() && mid_legal(A, *pl)) return VATS_KERNEL_MID;
   return VATS_KERNEL_TCGEN05;
 }
 
@@ -577,7 +681,14 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
   int auto_choice = choose_kernel(A, &pl);
-  if (kernel == VATS_KERNEL_AUTO) kernel = auto_choice;
+  if (kernel == VATS_KERNEL_AUTO) {
+    kernel = auto_choice;
+    if (kernel == VATS_KERNEL_MID) {
+      const int rc2 = launch_mid(A, pl, st);
+      if (rc2 >= 0) return rc2;
+      kernel = VATS_KERNEL_TCGEN05;   // K / V of one group do not fit shared memory
+    }
+  }
   if (kernel == VATS_KERNEL_TCGEN05) {
     if (!tc_legal(A, &pl))
       return fail(VATS_ERR_UNSUPPORTED,
@@ -585,6 +696,16 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
                   "4-byte aligned bases)",
                   A.hd);
     return launch_tc(A, pl, st);
+  }
+  if (kernel == VATS_KERNEL_MID) {
+    if (!tc_legal(A, &pl) || !mid_legal(A, pl))
+      return fail(VATS_ERR_UNSUPPORTED,
+                  "geometry not supported by the resident-K/V kernel (need 1 <= Tk <= 256, even hd <= 128, even strides, "
+                  "4-byte aligned bases; got Tk=%d hd=%d)", A.Tk, A.hd);
+    const int rc2 = launch_mid(A, pl, st);
+    if (rc2 >= 0) return rc2;
+    return fail(VATS_ERR_UNSUPPORTED, "resident-K/V kernel: K / V of one KV group do not fit shared memory (Tk=%d hd=%d)",
+                A.Tk, A.hd);
   }
   if (kernel == VATS_KERNEL_SIMT) {
     const int rc = launch_short(A, st);

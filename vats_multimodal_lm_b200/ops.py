@@ -19,11 +19,12 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
 KERNEL_SIMT = _ffi.KERNEL_SIMT
+KERNEL_MID = _ffi.KERNEL_MID
 
 
 def _require_cuda_bf16(name: str, t: torch.Tensor) -> None:
