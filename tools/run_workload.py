@@ -25,6 +25,8 @@ W = {
     "cfg4b": (12544, 8, 32, 8, 66, False, -1),
     "cfg5": (1, 32768, 32, 8, 128, True, 4096),
     "cfg5b2": (2, 32768, 32, 8, 128, True, 4096),
+    "cfg1s": (1, 384, 24, 8, 60, True, 384),
+    "cfg1t": (1, 32, 24, 8, 60, True, 384),
 }
 
 
@@ -40,6 +42,12 @@ def main():
     else:
         N, T, H, G, hd, causal, left = W[name]
         q, k, v = rnd((N, T, H, hd), 1, True), rnd((N, T, G, hd), 2, True), rnd((N, T, G, hd), 3, False)
+        if "--module-layout" in sys.argv and hd % 8 != 0:   # head stride padded to 8 elements, as the modules produce
+            def pad(x):
+                buf = torch.zeros(*x.shape[:-1], (hd + 7) // 8 * 8, dtype=x.dtype, device="cuda")
+                buf[..., :hd] = x
+                return buf[..., :hd]
+            q, k, v = pad(q), pad(k), pad(v)
         f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0)
         for _ in range(reps):
             o = f()
@@ -47,11 +55,18 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if "--flush" in sys.argv else None
+            tot = 0.0
             for _ in range(20):
+                if flush is not None:
+                    flush.zero_()
+                e0.record()
                 o = f()
-            e1.record()
-            torch.cuda.synchronize()
-            print(name, "ms/call", e0.elapsed_time(e1) / 20)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            from vats_multimodal_lm_b200 import _ffi
+            print(name, "ms/call", tot / 20, "kernel", _ffi.last_kernel())
     torch.cuda.synchronize()
     print(name, "ok", float(o.float().abs().mean()))
 

@@ -11,12 +11,14 @@ CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["vats_attn.cu"]
 HEADERS = ["ptx.cuh", "mask.cuh", "decode.cuh", "prefill_simt.cuh", "prefill_tc.cuh", "prefill_short.cuh", "prefill_mid.cuh", "decode_mma.cuh", "decode_prepare.cuh", "repack.cuh",
            os.path.join("..", "..", "include", "vats_attn.h")]
-OUT = os.path.join(CSRC, "libvats_attn.so")
+# VATS_BUILD_OUT: build a variant (e.g. VATS_ENABLE_TRACE=1) next to the product library instead of over it
+OUT = os.environ.get("VATS_BUILD_OUT") or os.path.join(CSRC, "libvats_attn.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "--use_fast_math", "-Xptxas", "-v", *([f"-DVATS_MBAR_TIMEOUT_CYCLES={os.environ['VATS_MBAR_TIMEOUT_CYCLES']}"] if os.environ.get("VATS_MBAR_TIMEOUT_CYCLES") else []),
     *(["-DVATS_ENABLE_TRACE"] if os.environ.get("VATS_ENABLE_TRACE") else []),
+    *(["-DVATS_MBAR_DEBUG"] if os.environ.get("VATS_MBAR_DEBUG") else []),
 ]
 
 

@@ -11,26 +11,35 @@
 //   * the 128 rows of a tile are (token, head) pairs: the H/G query heads of the group are packed into the M dimension
 //     (TMA box {64, heads, 128/heads}), so 196 tokens x 4 heads are 7 tiles instead of 8 and the tile's rows are
 //     contiguous in q and o;
-//   * two tile slots ping-pong: while one warpgroup runs its exponentials (the MUFU pipe is the co-critical resource at
-//     these shapes: 128 x 208 ex2 per tile = 1 664 cycles per SM sub-partition) the other slot's MMAs, TMEM traffic
-//     and write-out proceed.
+//   * a tile's row is split between TWO threads (column halves, warpgroups A and B): each keeps its <= 128 logits in
+//     registers, so S is read from TMEM exactly once (TMEM reads run at 64 B/clk per SM sub-partition — a second
+//     pass over S costs as much as the exponentials); the halves exchange the row maximum through shared memory;
+//   * the write-out has its own warpgroup, so the exponentials of tile f+1 (the MUFU pipe is the co-critical
+//     resource here: 128 x 208 ex2 per tile) overlap P.V, the TMEM read of O and the TMA store of tile f;
+//   * two TMEM tile slots ping-pong, so the MMAs of one tile run under the softmax of the other.
+// (First version, measured on B200: one warpgroup per slot doing two TMEM passes and its own epilogue — every phase
+// ran latency-bound with one active warp per sub-partition: cfg3 0.218 ms, no better than the 128 x 128 tile kernel.)
 //
-// Persistent CTAs (one per SM) walk the (sequence, KV group) items round-robin.
-//   warps 0-3 / 4-7  softmax warpgroup of slot 0 / 1: thread r owns tile row r (TMEM lane r)
-//   warps 8, 9, 10   TMA producers (one lane each): K ring, V ring, Q tiles
-//                    (kLdg instantiation: 96 loader threads stage K, Q, V with cp.async — rows TMA cannot address,
-//                    e.g. dense head_dim 66: 132-byte rows)
-//   warp 11          MMA issuer: S(f) = Q.K^T (SS), O(f) = P.V (TS, P from TMEM), in the order S(0) S(1) PV(0) S(2) PV(1) ...
-// TMEM: slot s owns columns [256 s, 256 s + 256): S in [0, n_pad); P (bf16) is written over S[0, n_pad/2) chunk by
-// chunk behind the softmax's second read pass; O accumulates in [o_off, o_off + hd_pad) with o_off = ceil16(n_pad/2),
-// i.e. inside the (by then consumed) upper half of S.
+// Persistent CTAs (one per SM, 16 warps) walk the (sequence, KV group) items round-robin.
+//   warps 0-3 / 4-7   softmax warpgroups A / B: thread r of each owns tile row r (TMEM lane r), A the columns
+//                     [0, cols_a), B the columns [cols_a, n_pad)
+//   warps 8-11        epilogue warpgroup: O from TMEM, 1/l, bf16, staging tile, TMA store (or coalesced stores)
+//   warps 12, 13, 14  TMA producers (one lane each): K ring, V ring, Q tiles
+//                     (kLdg instantiation: 96 loader threads stage K, Q, V with cp.async — rows TMA cannot address,
+//                     e.g. dense head_dim 66: 132-byte rows)
+//   warp 15           MMA issuer: S(f) = Q.K^T (SS), O(f) = P.V (TS, P from TMEM), in the order S(0) S(1) PV(0) S(2) PV(1) ...
+// TMEM: slot s holds S in n_pad columns; P (bf16) is written over S[0, n_pad/2) once both halves hold their logits
+// in registers.  When 2 * n_pad + hd_pad <= 512 (ViT shapes: 2 * 208 + 80) there is ONE O accumulator behind the two
+// slots: S(f+2) then only waits for P.V(f) to have consumed P(f) — in-order on the tensor pipe — and not for the
+// epilogue to drain O(f), which takes the TMEM read of O (64 B/clk) out of the S -> softmax -> P.V -> S loop.  Otherwise
+// (256 keys x hd 128) O accumulates inside the slot, in the consumed upper half of S, at o_off = ceil16(n_pad/2).
 #pragma once
 #include "mask.cuh"
 #include "prefill_tc.cuh"  // PrefillParams, tc_fastdiv, cp.async helpers, setmaxnreg, kTcOStageBytes
 
 namespace vats {
 
-constexpr int kMidThreads = 384;
+constexpr int kMidThreads = 512;
 constexpr int kMidLoaderThreads = 96;
 constexpr int kMidMaxKv = 4;        // deepest K / V ring
 constexpr int kMidSlotCols = 256;   // TMEM columns per tile slot
@@ -41,7 +50,12 @@ struct MidParams {
   int hd_pad;          // head dim rounded up to 16 (MMA K of S, MMA N of P.V)
   int regions;         // ceil(hd_pad / 64) 128-byte swizzle regions per row
   int n_pad;           // keys rounded up to 16 (MMA N of S, K extent of P.V), <= 256
-  int o_off;           // TMEM column of O inside a slot
+  int cols_a;          // columns of a row owned by softmax warpgroup A (multiple of 16, <= 128); B owns the rest
+  int slot_cols;       // TMEM columns between the two tile slots
+  int o_shared;        // 1: ONE O accumulator behind both S slots (2 * n_pad + hd_pad <= 512): a slot is free for the
+                       //    next S as soon as its P was consumed; 0: O lives inside each slot's consumed S columns
+  int o_off;           // TMEM column of O: absolute (o_shared) or relative to the slot
+  int o_bufs;          // staging tiles per epilogue warp (2 = the TMA read of one chunk overlaps staging the next)
   int pack, pack_shift;  // query heads packed into one tile (power of two <= 32), its log2
   int tok_per_tile;    // 128 >> pack_shift
   int q_tiles;         // ceil(Tq / tok_per_tile)
@@ -50,22 +64,50 @@ struct MidParams {
   int num_items;       // N * G
   int nkv;             // K / V ring depth
   int ldg_vec;         // kLdg: 32-bit words per cp.async copy (1 or 2)
-  int o_stage;         // 1 = TMA tile stores, 2 = coalesced 32-bit stores from the staging tile
+  int o_stage;         // 1 = 128B-swizzled staging + TMA tile stores (one per 64 columns); 2 = the same staging, written
+                       // out with coalesced 32-bit stores; 3 = dense row staging + ONE untiled TMA store per warp
+                       // (O dense within a token: the warp's 32 rows are 32/pack runs of pack*hd elements)
   int simple_mask;     // 1: no band, no q_valid / k_valid — only the columns >= Tk are masked
   unsigned div_g[2], div_qt[2];
+  unsigned long long* trace;   // debug timeline (VATS_ENABLE_TRACE builds): block 0 appends (tag, clock) records
+  int trace_cap;
 };
+
+#if defined(VATS_ENABLE_TRACE)
+struct MidTracer {
+  unsigned long long* base;
+  int n, cap;
+  __device__ __forceinline__ MidTracer(const MidParams& P, int role)
+      : base(P.trace != nullptr && blockIdx.x == 0 ? P.trace + (size_t)role * 2 * P.trace_cap : nullptr), n(0),
+        cap(P.trace_cap) {}
+  __device__ __forceinline__ void operator()(unsigned tag) {
+    if (base != nullptr && n < cap) {
+      base[2 * n] = tag;
+      base[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+};
+#else
+struct MidTracer {
+  __device__ __forceinline__ MidTracer(const MidParams&, int) {}
+  __device__ __forceinline__ void operator()(unsigned) {}
+};
+#endif
 
 struct MidBarriers {
   uint64_t q_full[2], q_empty[2], s_full[2], p_full[2], o_full[2], o_empty[2];
   uint64_t k_full[kMidMaxKv], k_empty[kMidMaxKv], v_full[kMidMaxKv], v_empty[kMidMaxKv];
-  uint32_t kbits[8][8];   // per softmax warp: k_valid of the current item as bit words (generic-mask path)
+  float row_max[2][2][128];   // [slot][column half][row]: the halves' row maxima (raw logits)
+  float row_sum[2][2][128];   // [slot][column half][row]: the halves' row sums, read by the epilogue
+  uint32_t kbits[8][8];       // per softmax warp: k_valid of the current item as bit words (generic-mask path)
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-__host__ __device__ inline size_t mid_smem_bytes(int regions, int n_pad, int nkv) {
-  return (size_t)2 * regions * kMidQRegionBytes + (size_t)2 * nkv * regions * n_pad * 128 + 8 * kTcOStageBytes + 1024 +
-         sizeof(MidBarriers);
+__host__ __device__ inline size_t mid_smem_bytes(int regions, int n_pad, int nkv, int o_bufs) {
+  return (size_t)2 * regions * kMidQRegionBytes + (size_t)2 * nkv * regions * n_pad * 128 +
+         (size_t)4 * o_bufs * kTcOStageBytes + 1024 + sizeof(MidBarriers);
 }
 
 struct MidCursor {
@@ -119,86 +161,16 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 
-// NC columns of S (NC = 64, 32 or 16) starting at column c0 of this thread's row -> registers
-template <int NC>
-__device__ __forceinline__ void mid_ld_cols(uint32_t taddr, uint32_t* v) {
-  if (NC == 64) {
-    ptx::tmem_ld_32x32b_x32(taddr, v);
-    ptx::tmem_ld_32x32b_x32(taddr + 32, v + 32);
-  } else if (NC == 32) {
-    ptx::tmem_ld_32x32b_x32(taddr, v);
-  } else {
-    ptx::tmem_ld_32x32b_x16(taddr, v);
-  }
-  ptx::tmem_ld_wait();
+// 16-bit word of allowed columns [base, base + 16) for a row whose allowed keys are [lo, hi]
+__device__ __forceinline__ uint32_t mid_range16(int lo, int hi, int base) {
+  const int l = lo - base, h = hi - base;
+  const uint32_t ml = l <= 0 ? 0xffffu : (l >= 16 ? 0u : (0xffffu << l) & 0xffffu);
+  const uint32_t mh = h >= 15 ? 0xffffu : (h < 0 ? 0u : 0xffffu >> (15 - h));
+  return ml & mh;
 }
 
-// Mask the NC values of one row in place (-inf where the key is not allowed).
-template <int NC>
-__device__ __forceinline__ void mid_apply_mask(uint32_t* v, int c0, int lo, int hi, const uint32_t* kb, bool use_kb) {
-#pragma unroll
-  for (int w = 0; w < (NC + 31) / 32; ++w) {
-    uint32_t bits = mid_range_word(lo, hi, c0 + 32 * w);
-    if (use_kb) bits &= kb[(c0 >> 5) + w] >> (c0 & 16);   // (c0 & 16 != 0 only for the 16-column tail block)
-    if (NC == 16) bits |= 0xffff0000u;
-    if (bits != 0xffffffffu) {
-#pragma unroll
-      for (int i = 0; i < (NC < 32 ? NC : 32); ++i)
-        if (!((bits >> i) & 1u)) v[32 * w + i] = 0xff800000u;
-    }
-  }
-}
-
-// pass 1: running row maximum (raw logits) over one block of columns
-template <int NC>
-__device__ __forceinline__ float mid_pass_max(uint32_t tS, int c0, int lo, int hi, const uint32_t* kb, bool use_kb,
-                                              float m) {
-  uint32_t v[NC];
-  mid_ld_cols<NC>(tS + (uint32_t)c0, v);
-  mid_apply_mask<NC>(v, c0, lo, hi, kb, use_kb);
-  float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < NC; i += 8) {
-    m0 = mid_max3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-    m1 = mid_max3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-    m2 = mid_max3(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-    m3 = mid_max3(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
-
-// pass 2: p = exp2(s * scale_log2 - m), row sum, bf16 pack, P written over S[c0/2, c0/2 + NC/2)
-template <int NC>
-__device__ __forceinline__ float mid_pass_exp(uint32_t tS, int c0, int lo, int hi, const uint32_t* kb, bool use_kb,
-                                              float scale_log2, float neg_m) {
-  using namespace ptx;
-  uint32_t v[NC];
-  mid_ld_cols<NC>(tS + (uint32_t)c0, v);
-  mid_apply_mask<NC>(v, c0, lo, hi, kb, use_kb);
-  const float2 sc2 = make_float2(scale_log2, scale_log2);
-  const float2 nm2 = make_float2(neg_m, neg_m);
-  float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-  uint32_t pk[NC / 2];
-#pragma unroll
-  for (int c = 0; c < NC; c += 4) {
-    const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), sc2, nm2);
-    const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), sc2, nm2);
-    const float2 p0 = make_float2(ex2(x0.x), ex2(x0.y));
-    const float2 p1 = make_float2(ex2(x1.x), ex2(x1.y));
-    sum_a = __fadd2_rn(sum_a, p0);
-    sum_b = __fadd2_rn(sum_b, p1);
-    pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
-    pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-  }
-  const uint32_t tP = tS + (uint32_t)(c0 >> 1);
-  if (NC == 64) {
-    tmem_st_32x32b_x32(tP, pk);
-  } else if (NC == 32) {
-    tmem_st_32x32b_x16(tP, pk);
-  } else {
-    tmem_st_32x32b_x8(tP, pk);
-  }
-  return (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+__device__ __forceinline__ void mid_named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // Stage `rows_pad` rows x hd of bf16 into 128B-swizzled regions (the layout a SWIZZLE_128B TMA box {64, ..., rows}
@@ -232,7 +204,11 @@ __device__ __forceinline__ void mid_cpasync_rows(uint32_t dst, RowPtr row_ptr, c
   }
 }
 
-template <bool kLdg>
+// kLdg: Q / K / V staged with cp.async instead of TMA.  kSimple: no band, no q_valid / k_valid — the only masked
+// columns are those past the end of the sequence (the ViT passes); the generic per-row predicate is then not even
+// compiled in (the softmax warps are instruction-fetch-bound: every instruction and branch removed from the per-tile
+// path counts).
+template <bool kLdg, bool kSimple>
 __global__ void __launch_bounds__(kMidThreads, 1)
 prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -251,24 +227,24 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
   const uint32_t sV = sK + (uint32_t)P.nkv * kv_tile;
   const uint32_t sO = sV + (uint32_t)P.nkv * kv_tile;
   MidBarriers* bars = reinterpret_cast<MidBarriers*>(smem_raw + (base - raw) + (size_t)2 * q_tile +
-                                                     (size_t)2 * P.nkv * kv_tile + 8 * kTcOStageBytes);
+                                                     (size_t)2 * P.nkv * kv_tile + (size_t)4 * P.o_bufs * kTcOStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     if (!kLdg) {
       prefetch_tmap(&tmap_q);
       prefetch_tmap(&tmap_k);
       prefetch_tmap(&tmap_v);
     }
-    if (P.o_stage == 1) prefetch_tmap(&tmap_o);
+    if (P.o_stage == 1 || P.o_stage == 3) prefetch_tmap(&tmap_o);
     const uint32_t load_arrivals = kLdg ? kMidLoaderThreads : 1;
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->q_full[s]), load_arrivals);
       mbar_init(smem_u32(&bars->q_empty[s]), 1);
       mbar_init(smem_u32(&bars->s_full[s]), 1);
-      mbar_init(smem_u32(&bars->p_full[s]), 128);
+      mbar_init(smem_u32(&bars->p_full[s]), 256);
       mbar_init(smem_u32(&bars->o_full[s]), 1);
       mbar_init(smem_u32(&bars->o_empty[s]), 128);
     }
@@ -280,7 +256,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
     }
     fence_mbar_init();
   }
-  if (warp == 11) {
+  if (warp == 15) {
     tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tmem_relinquish();
   }
@@ -289,26 +265,28 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp >= 8) {
-    setmaxnreg_dec<80>();
-    if (warp <= 10) {
+  if (warp >= 12) {
+    setmaxnreg_dec<64>();
+    if (warp <= 14) {
       if (!kLdg) {
         // ------------------------------------------------------------------ TMA producers
         if (lane == 0) {
-          if (warp == 10) {
+          MidTracer trace(P, 0);
+          if (warp == 14) {
             MidCursor c{(int)blockIdx.x, 0};
             for (uint32_t f = 0; c.item < P.num_items; ++f) {
               const MidTile t = mid_decode(P, c);
               const uint32_t s = f & 1u, u = f >> 1;
-              mbar_wait(smem_u32(&bars->q_empty[s]), (u & 1u) ^ 1u, 0x300u);
+              mbar_wait_relaxed(smem_u32(&bars->q_empty[s]), (u & 1u) ^ 1u);
               const uint32_t bar = smem_u32(&bars->q_full[s]);
               mbar_expect_tx(bar, q_tile);
               for (int r = 0; r < P.regions; ++r)
                 tma_load_4d(sQ + s * q_tile + (uint32_t)r * kMidQRegionBytes, &tmap_q, bar, 64 * r, t.head0, t.q0, t.n);
+              trace(0x300u + (f & 15u));
               mid_advance(P, c, 1);
             }
           } else {
-            const bool is_k = warp == 8;
+            const bool is_k = warp == 12;
             const CUtensorMap* tm = is_k ? &tmap_k : &tmap_v;
             uint64_t* full = is_k ? bars->k_full : bars->v_full;
             uint64_t* empty = is_k ? bars->k_empty : bars->v_empty;
@@ -318,7 +296,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
             for (int item = (int)blockIdx.x; item < P.num_items; item += (int)gridDim.x) {
               unsigned n, g;
               tc_fastdiv((unsigned)item, P.div_g, (unsigned)a.G, &n, &g);
-              mbar_wait(smem_u32(&empty[slot]), ph ^ 1u, 0x310u);
+              mbar_wait_relaxed(smem_u32(&empty[slot]), ph ^ 1u);
               const uint32_t bar = smem_u32(&full[slot]);
               mbar_expect_tx(bar, kv_tile);
               for (int r = 0; r < P.regions; ++r)
@@ -331,7 +309,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         // ------------------------------------------------------------------ cp.async loaders (96 threads), in the
         // order the MMA warp consumes: K, Q(0), Q(1), V, Q(2), ... per item.  A tile is signalled only after the
         // copies of the next one were issued, so two tiles are in flight per thread.
-        const int ltid = (int)threadIdx.x - 8 * 32;
+        const int ltid = (int)threadIdx.x - 12 * 32;
         uint32_t pending = 0u;
         // A tile's arrival is deferred until the next tile's copies are in flight — but never across a wait that may
         // depend on it (with a one-deep K ring the next item's k_empty needs S of the tile still pending here).
@@ -409,6 +387,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
     } else {
       // -------------------------------------------------------------------- MMA issuer (all lanes convergent)
       const uint32_t leader = elect_one() ? 1u : 0u;
+      MidTracer trace(P, 1);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_s = make_idesc_bf16(128, P.n_pad, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, P.hd_pad, 0, 1);
@@ -430,15 +409,19 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         if (f >= 2) {
           // ---- O(f-2) = P.V
           const uint32_t s = (uint32_t)f & 1u, u = (uint32_t)(f - 2) >> 1;
-          mbar_wait(smem_u32(&bars->p_full[s]), u & 1u, 0x100u);
+          if (leader) trace(0x100u + ((uint32_t)f & 15u));
+          mbar_wait_relaxed(smem_u32(&bars->p_full[s]), u & 1u, 20);
           if (pv_tt == 0) mbar_wait(smem_u32(&bars->v_full[vs]), vph, 0x101u);
+          if (P.o_shared && f >= 3)   // the one accumulator: the epilogue must have read O(f-3) out
+            mbar_wait(smem_u32(&bars->o_empty[s ^ 1u]), ((uint32_t)(f - 3) >> 1) & 1u, 0x102u);
+          if (leader) trace(0x110u + ((uint32_t)f & 15u));
           tc_fence_after();
-          const uint32_t tP = tmem_u + s * kMidSlotCols;
+          const uint32_t tP = tmem_u + s * (uint32_t)P.slot_cols;
+          const uint32_t tD = P.o_shared ? tmem_u + (uint32_t)P.o_off : tP + (uint32_t)P.o_off;
           const uint32_t v_lo = v_lo_base + (uint32_t)vs * kv_step;
           uint32_t acc = 0u;
           for (int k = 0; k < ksteps_o; ++k) {
-            mma_ts_lohi(tP + (uint32_t)P.o_off, tP + (uint32_t)k * 8u, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc,
-                        leader);
+            mma_ts_lohi(tD, tP + (uint32_t)k * 8u, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc, leader);
             acc = 1u;
           }
           tc_commit_pred(smem_u32(&bars->o_full[s]), leader);
@@ -451,14 +434,18 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         if (f < total) {
           // ---- S(f) = Q.K^T
           const uint32_t s = (uint32_t)f & 1u, u = (uint32_t)f >> 1;
+          if (leader) trace(0x120u + ((uint32_t)f & 15u));
           mbar_wait(smem_u32(&bars->q_full[s]), u & 1u, 0x110u);
           if (s_tt == 0) mbar_wait(smem_u32(&bars->k_full[ks]), kph, 0x111u);
-          if (u > 0) mbar_wait(smem_u32(&bars->o_empty[s]), (u - 1u) & 1u, 0x112u);   // the slot's previous O was read out
+          if (leader) trace(0x130u + ((uint32_t)f & 15u));
+          if (!P.o_shared && u > 0)   // O inside the slot: its previous O must have been read out
+            mbar_wait(smem_u32(&bars->o_empty[s]), (u - 1u) & 1u, 0x112u);
+          if (leader) trace(0x140u + ((uint32_t)f & 15u));
           tc_fence_after();
           uint32_t ql = q_lo[s], kl = k_lo_base + (uint32_t)ks * kv_step;
           uint32_t acc = 0u;
           for (int k = 0; k < ksteps_s; ++k) {
-            mma_ss_lohi(tmem_u + s * kMidSlotCols, ql, hi_sw, kl, hi_sw, idesc_s, acc, leader);
+            mma_ss_lohi(tmem_u + s * (uint32_t)P.slot_cols, ql, hi_sw, kl, hi_sw, idesc_s, acc, leader);
             acc = 1u;
             if ((k & 3) == 3) {
               ql += rq - 6u;
@@ -478,149 +465,346 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         }
       }
     }
-  } else {
-    // ====================================================================== softmax warpgroups (slot = warp / 4)
-    setmaxnreg_inc<208>();
-    const uint32_t slot = (uint32_t)warp >> 2;
+  } else if (warp >= 8) {
+    // ====================================================================== epilogue warpgroup (warps 8-11)
+    setmaxnreg_dec<96>();
     const int wq = warp & 3;
-    const int r = (int)threadIdx.x & 127;
+    const int r = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const uint32_t tS = tmem + lane_base + slot * kMidSlotCols;
-    const uint32_t tO = tS + (uint32_t)P.o_off;
-    const uint32_t stage = sO + (uint32_t)warp * kTcOStageBytes;
-    uint32_t* kb = bars->kbits[warp];
-    const bool use_kb = a.k_valid != nullptr;
-
+    const uint32_t stage0 = sO + (uint32_t)(wq * P.o_bufs) * kTcOStageBytes;
+    MidTracer trace(P, 3);
+    uint32_t nstore = 0u;   // staging tiles used so far (alternates the two buffers)
     MidCursor c{(int)blockIdx.x, 0};
-    mid_advance(P, c, (int)slot);
-    for (uint32_t u = 0; c.item < P.num_items; ++u, mid_advance(P, c, 2)) {
+    for (uint32_t f = 0; c.item < P.num_items; ++f, mid_advance(P, c, 1)) {
       const MidTile t = mid_decode(P, c);
+      const uint32_t slot = f & 1u, u = f >> 1;
       const int tok = t.q0 + (r >> P.pack_shift);
-      const int head = t.head0 + (r & (P.pack - 1));
       const int tok_w = t.q0 + ((wq * 32) >> P.pack_shift);   // first token of this warp's 32 rows
       const bool warp_live = tok_w < a.Tq;
+      const uint32_t tO = tmem + lane_base + (P.o_shared ? 0u : slot * (uint32_t)P.slot_cols) + (uint32_t)P.o_off;
+      bool qok = tok < a.Tq;
+      if (qok && a.q_valid != nullptr) qok = a.q_valid[(long long)t.n * a.Tq + tok] != 0;
+
+      if (r == 0) trace(0x240u + (f & 15u));
+      mbar_wait_relaxed(smem_u32(&bars->o_full[slot]), u & 1u, 40);
+      if (r == 0) trace(0x250u + (f & 15u));
+      tc_fence_after();
+      const float l_sum = bars->row_sum[slot][0][r] + bars->row_sum[slot][1][r];
+      const float inv = (qok && l_sum > 0.f) ? 1.f / l_sum : 0.f;
+      if (P.o_stage == 3) {
+        // ---- dense row staging: lane's row at stage + lane * hd * 2 (exactly the box {pack*hd/2 words, 32/pack tokens}
+        //      of the untiled tensor map), both 64-column halves, then ONE TMA store for the warp's 32 rows
+        const uint32_t stage = stage0 + (P.o_bufs == 2 && a.hd <= 64 ? (nstore & 1u) * kTcOStageBytes : 0u);
+        const uint32_t row_bytes = (uint32_t)a.hd * 2u;
+        const bool vec16 = (row_bytes & 15u) == 0u;
+        const int npieces = (P.hd_pad + 31) >> 5;   // 32 accumulator columns at a time (the epilogue warps run on 96 registers)
+        if (warp_live) {
+          if (lane == 0) {   // the store that last read this staging tile must be done with it
+            if (P.o_bufs == 2 && a.hd <= 64)
+              bulk_wait_group_read<1>();
+            else
+              bulk_wait_group_read0();
+          }
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int pi = 0; pi < 4; ++pi) {
+          if (pi < npieces) {
+            const int cb = pi * 32;
+            if (warp_live) {
+              // (both halves are always loaded: the slot's 256 columns exist, columns >= hd are never stored)
+              uint32_t acc[32];
+              tmem_ld_32x32b_x16(tO + cb, acc);
+              tmem_ld_32x32b_x16(tO + cb + 16, acc + 16);
+              tmem_ld_wait();
+              if (pi == npieces - 1) {   // the last columns of O are in registers: the slot may take the next S
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->o_empty[slot]));
+              }
+              const uint32_t dst_row = stage + (uint32_t)lane * row_bytes + (uint32_t)cb * 2u;
+#pragma unroll
+              for (int uu = 0; uu < 4; ++uu) {
+                const int col = cb + uu * 8;
+                const uint32_t x = pack_bf16x2(__uint_as_float(acc[8 * uu + 0]) * inv, __uint_as_float(acc[8 * uu + 1]) * inv);
+                const uint32_t y = pack_bf16x2(__uint_as_float(acc[8 * uu + 2]) * inv, __uint_as_float(acc[8 * uu + 3]) * inv);
+                const uint32_t z = pack_bf16x2(__uint_as_float(acc[8 * uu + 4]) * inv, __uint_as_float(acc[8 * uu + 5]) * inv);
+                const uint32_t w = pack_bf16x2(__uint_as_float(acc[8 * uu + 6]) * inv, __uint_as_float(acc[8 * uu + 7]) * inv);
+                const uint32_t dst = dst_row + (uint32_t)uu * 16u;
+                if (vec16) {
+                  if (col < a.hd)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+                } else {   // rows only 4-byte aligned (hd 66, 60): word stores, conflict-free for an odd word pitch
+                  if (col < a.hd) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(x) : "memory");
+                  if (col + 2 < a.hd) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 4u), "r"(y) : "memory");
+                  if (col + 4 < a.hd) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 8u), "r"(z) : "memory");
+                  if (col + 6 < a.hd) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 12u), "r"(w) : "memory");
+                }
+              }
+            } else if (pi == npieces - 1) {
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->o_empty[slot]));
+            }
+          }
+        }
+        if (warp_live) {
+          ++nstore;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_o, stage, (t.head0 * a.hd) >> 1, tok_w, t.n);
+            bulk_commit_group();
+          }
+        }
+      } else {
+#pragma unroll
+      for (int cbi = 0; cbi < 2; ++cbi) {
+        const int cb = cbi * 64;
+        if (cb >= P.hd_pad) continue;
+        uint32_t acc[64];
+        if (warp_live) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (cb + i * 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + cb + i * 16, acc + i * 16);
+          tmem_ld_wait();
+        }
+        if (cb + 64 >= P.hd_pad) {   // the last columns of O are in registers: the slot may take the next S
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->o_empty[slot]));
+        }
+        if (!warp_live) continue;
+        const uint32_t stage = stage0 + (P.o_bufs == 2 ? (nstore & 1u) * kTcOStageBytes : 0u);
+        ++nstore;
+        if (P.o_stage == 1 && lane == 0) {   // the TMA store that last read this staging tile must be done with it
+          if (P.o_bufs == 2)
+            bulk_wait_group_read<1>();
+          else
+            bulk_wait_group_read0();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          if (cb + uu * 8 < P.hd_pad) {
+            const uint32_t x = pack_bf16x2(__uint_as_float(acc[8 * uu + 0]) * inv, __uint_as_float(acc[8 * uu + 1]) * inv);
+            const uint32_t y = pack_bf16x2(__uint_as_float(acc[8 * uu + 2]) * inv, __uint_as_float(acc[8 * uu + 3]) * inv);
+            const uint32_t z = pack_bf16x2(__uint_as_float(acc[8 * uu + 4]) * inv, __uint_as_float(acc[8 * uu + 5]) * inv);
+            const uint32_t w = pack_bf16x2(__uint_as_float(acc[8 * uu + 6]) * inv, __uint_as_float(acc[8 * uu + 7]) * inv);
+            const uint32_t dst = stage + (uint32_t)lane * 128u + (((uint32_t)uu ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+          }
+        }
+        if (P.o_stage == 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmap_o, stage, cb, t.head0, tok_w, t.n);
+            bulk_commit_group();
+          }
+        } else {
+          __syncwarp();
+          const int wv = (a.hd - cb >= 64 ? 64 : a.hd - cb) >> 1;   // valid 32-bit words per row in this chunk
+          if (wv > 0) {
+            const int dq = 32 / wv, dr = 32 % wv;
+            int row = lane / wv, w = lane - row * wv;
+            while (row < 32) {
+              const int rt = tok_w + (row >> P.pack_shift);
+              if (rt < a.Tq) {
+                const uint32_t src = stage + (uint32_t)row * 128u + ((((uint32_t)w >> 2) ^ ((uint32_t)row & 7u)) << 4) +
+                                     (((uint32_t)w & 3u) << 2);
+                uint32_t val;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val) : "r"(src) : "memory");
+                uint32_t* orow = reinterpret_cast<uint32_t*>(a.o + (long long)t.n * a.os_n + (long long)rt * a.os_t +
+                                                             (long long)(t.head0 + (row & (P.pack - 1))) * a.os_h + cb);
+                orow[w] = val;
+              }
+              w += dr;
+              row += dq;
+              if (w >= wv) {
+                w -= wv;
+                ++row;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      }
+      if (r == 0) trace(0x260u + (f & 15u));
+    }
+    if ((P.o_stage == 1 || P.o_stage == 3) && lane == 0) bulk_wait_group0();   // staged O tiles must be out before the CTA's smem goes away
+  } else {
+    // ====================================================================== softmax warpgroups A (warps 0-3), B (4-7)
+    setmaxnreg_inc<176>();
+    const int half = warp >> 2;
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const int my_c0 = half ? P.cols_a : 0;                       // first column of this thread's share of the row
+    const int my_n = half ? P.n_pad - P.cols_a : P.cols_a;      // its width (multiple of 16, possibly 0 for B)
+    uint32_t* kb = bars->kbits[warp];
+    const bool use_kb = a.k_valid != nullptr;
+    MidTracer trace(P, 2);
+
+    // This thread's share of a row lives in v[] (one TMEM read per tile).  While the exponentials of tile f run, each
+    // group of 16 registers is refilled with the same columns of S(f+1) as soon as it has been consumed: the TMEM read
+    // (64 B/clk per SM — as long as the exponentials themselves) hides behind the MUFU work instead of preceding it.
+    uint32_t v[128];
+    bool prefetched = false;     // v[] already holds (or is receiving) this tile's logits
+    MidCursor c{(int)blockIdx.x, 0};
+    MidTile t = mid_decode(P, c);
+    for (uint32_t f = 0; c.item < P.num_items; ++f) {
+      const uint32_t slot = f & 1u, u = f >> 1;
+      const uint32_t tS = tmem + lane_base + slot * (uint32_t)P.slot_cols;
+      const int tok = t.q0 + (r >> P.pack_shift);
+      const int tok_w = t.q0 + ((wq * 32) >> P.pack_shift);
+      const bool warp_live = tok_w < a.Tq;
+      const int tile_n = t.n;
+      // the next tile of this CTA (its slot is the other one); the prefetch needs the same warp to be live there
+      mid_advance(P, c, 1);
+      bool next_live = false;
+      if (c.item < P.num_items) {
+        t = mid_decode(P, c);
+        next_live = (t.q0 + ((wq * 32) >> P.pack_shift)) < a.Tq;
+      }
 
       int lo = 0, hi = a.Tk - 1;
-      if (!P.simple_mask && tok < a.Tq) {
+      if (!kSimple && tok < a.Tq) {
         const long long l = key_lo(a.mask, tok), h = key_hi(a.mask, tok);
         lo = l < 0 ? 0 : (l > 256 ? 256 : (int)l);
         hi = h < -1 ? -1 : (int)h;   // key_hi is already <= Tk - 1
       }
-      if (use_kb && warp_live) {
+      if (!kSimple && use_kb && warp_live) {
         for (int w = 0; w < (P.n_pad + 31) / 32; ++w) {
           const int key = w * 32 + lane;
-          const bool ok = key < a.Tk && a.k_valid[(long long)t.n * a.Tk + key] != 0;
+          const bool ok = key < a.Tk && a.k_valid[(long long)tile_n * a.Tk + key] != 0;
           const uint32_t bits = __ballot_sync(0xffffffffu, ok);
           if (lane == 0) kb[w] = bits;
         }
         __syncwarp();
       }
 
-      mbar_wait(smem_u32(&bars->s_full[slot]), u & 1u, 0x200u);
-      tc_fence_after();
-      float l_sum = 0.f;
+      if (r == 0 && half == 0) trace(0x200u + (f & 15u));
+      if (!prefetched) {   // (a prefetching tile already waited for this S)
+        mbar_wait(smem_u32(&bars->s_full[slot]), u & 1u, 0x200u);
+        tc_fence_after();
+      }
+      if (r == 0 && half == 0) trace(0x210u + (f & 15u));
+
+      // ---- this thread's share of the row -> registers (one TMEM read), mask, local maximum
+      float m = -INFINITY;
       if (warp_live) {
-        // ---- pass 1: exact row maximum
-        float m = -INFINITY;
-        int c0 = 0;
-        for (; c0 + 64 <= P.n_pad; c0 += 64) m = mid_pass_max<64>(tS, c0, lo, hi, kb, use_kb, m);
-        if (P.n_pad & 32) {
-          m = mid_pass_max<32>(tS, c0, lo, hi, kb, use_kb, m);
-          c0 += 32;
+        if (!prefetched) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 16 < my_n) tmem_ld_32x32b_x16(tS + (uint32_t)(my_c0 + g * 16), v + g * 16);
         }
-        if (P.n_pad & 16) m = mid_pass_max<16>(tS, c0, lo, hi, kb, use_kb, m);
-        // ---- pass 2: exponentials, row sum, P over S
+        tmem_ld_wait();
+        if (r == 0 && half == 0) trace(0x280u + (f & 15u));
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g * 16 < my_n) {
+            const int cg = my_c0 + g * 16;
+            if (kSimple) {
+              if (cg + 16 > a.Tk) {   // the group that holds the end of the sequence (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (cg + i >= a.Tk) v[g * 16 + i] = 0xff800000u;
+              }
+            } else {
+              uint32_t bits = mid_range16(lo, hi, cg);
+              if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
+              if (bits != 0xffffu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (!((bits >> i) & 1u)) v[g * 16 + i] = 0xff800000u;
+              }
+            }
+            m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 0]), __uint_as_float(v[g * 16 + 1]));
+            m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 2]), __uint_as_float(v[g * 16 + 3]));
+            m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 4]), __uint_as_float(v[g * 16 + 5]));
+            m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 6]), __uint_as_float(v[g * 16 + 7]));
+            m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 8]), __uint_as_float(v[g * 16 + 9]));
+            m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 10]), __uint_as_float(v[g * 16 + 11]));
+            m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 12]), __uint_as_float(v[g * 16 + 13]));
+            m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 14]), __uint_as_float(v[g * 16 + 15]));
+          }
+        }
+        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      // ---- row maximum across the two halves (also orders B's P stores behind A's TMEM reads and vice versa)
+      if (r == 0 && half == 0) trace(0x290u + (f & 15u));
+      bars->row_max[slot][half][r] = m;
+      mid_named_barrier(1, 256);
+      if (r == 0 && half == 0) trace(0x220u + (f & 15u));
+      if (warp_live) {
+        m = fmaxf(m, bars->row_max[slot][half ^ 1][r]);
         const float neg_m = (m == -INFINITY) ? 0.f : -m * a.scale_log2;
-        c0 = 0;
-        for (; c0 + 64 <= P.n_pad; c0 += 64) l_sum += mid_pass_exp<64>(tS, c0, lo, hi, kb, use_kb, a.scale_log2, neg_m);
-        if (P.n_pad & 32) {
-          l_sum += mid_pass_exp<32>(tS, c0, lo, hi, kb, use_kb, a.scale_log2, neg_m);
-          c0 += 32;
+        const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
+        const float2 nm2 = make_float2(neg_m, neg_m);
+        float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+        const uint32_t tP = tS + (uint32_t)(my_c0 >> 1);
+        const uint32_t tSn = tmem + lane_base + (slot ^ 1u) * (uint32_t)P.slot_cols + (uint32_t)my_c0;
+        // S(f+1) becomes ready somewhere inside this loop (it is issued behind P.V(f-1)): poll, and from then on refill
+        // every consumed group of registers with the same columns of the next tile
+        const uint32_t next_bar = smem_u32(&bars->s_full[slot ^ 1u]);
+        const uint32_t next_par = ((f + 1u) >> 1) & 1u;
+        bool ready = false;
+        int skipped = 0;    // groups [0, skipped) were consumed before S(f+1) was ready (steady state: none)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g * 16 < my_n) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[g * 16 + i]), __uint_as_float(v[g * 16 + i + 1])), sc2, nm2);
+              const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[g * 16 + i + 2]), __uint_as_float(v[g * 16 + i + 3])), sc2, nm2);
+              const float2 p0 = make_float2(ex2(x0.x), ex2(x0.y));
+              const float2 p1 = make_float2(ex2(x1.x), ex2(x1.y));
+              sum_a = __fadd2_rn(sum_a, p0);
+              sum_b = __fadd2_rn(sum_b, p1);
+              pk[i >> 1] = pack_bf16x2(p0.x, p0.y);
+              pk[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+            }
+            tmem_st_32x32b_x8(tP + (uint32_t)(g * 8), pk);
+            if (next_live) {
+              if (!ready) {
+                ready = __all_sync(0xffffffffu, mbar_try_wait(next_bar, next_par));
+                if (ready) tc_fence_after();
+              }
+              if (ready)
+                tmem_ld_32x32b_x16(tSn + (uint32_t)(g * 16), v + g * 16);
+              else
+                skipped = g + 1;
+            }
+            if (r == 0 && half == 0 && (g == 0 || g == 3)) trace(0x2a0u + (uint32_t)g);
+          }
         }
-        if (P.n_pad & 16) l_sum += mid_pass_exp<16>(tS, c0, lo, hi, kb, use_kb, a.scale_log2, neg_m);
+        if (next_live) {   // whatever was consumed before S(f+1) arrived
+          if (!ready) {
+            mbar_wait(next_bar, next_par, 0x201u);
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int gg = 0; gg < 8; ++gg)
+            if (gg < skipped) tmem_ld_32x32b_x16(tSn + (uint32_t)(gg * 16), v + gg * 16);
+        }
+        bars->row_sum[slot][half][r] = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
         tmem_st_wait();
+        prefetched = next_live;
+      } else {
+        bars->row_sum[slot][half][r] = 0.f;
+        prefetched = false;
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->p_full[slot]));
-
-      // ---- epilogue: O / l -> bf16 -> staging tile -> global
-      mbar_wait(smem_u32(&bars->o_full[slot]), u & 1u, 0x210u);
-      tc_fence_after();
-      uint32_t acc[128];
-      if (warp_live) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 16 < P.hd_pad) tmem_ld_32x32b_x16(tO + i * 16, acc + i * 16);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->o_empty[slot]));
-      if (warp_live) {
-        bool qok = tok < a.Tq;
-        if (qok && a.q_valid != nullptr) qok = a.q_valid[(long long)t.n * a.Tq + tok] != 0;
-        const float inv = (qok && l_sum > 0.f) ? 1.f / l_sum : 0.f;
-#pragma unroll
-        for (int cbi = 0; cbi < 2; ++cbi) {
-          const int cb = cbi * 64;
-          if (cb >= P.hd_pad) continue;
-          if (P.o_stage == 1 && lane == 0) bulk_wait_group_read0();
-          __syncwarp();
-#pragma unroll
-          for (int uu = 0; uu < 8; ++uu) {
-            if (cb + uu * 8 < P.hd_pad) {
-              const uint32_t x = pack_bf16x2(__uint_as_float(acc[cb + 8 * uu + 0]) * inv, __uint_as_float(acc[cb + 8 * uu + 1]) * inv);
-              const uint32_t y = pack_bf16x2(__uint_as_float(acc[cb + 8 * uu + 2]) * inv, __uint_as_float(acc[cb + 8 * uu + 3]) * inv);
-              const uint32_t z = pack_bf16x2(__uint_as_float(acc[cb + 8 * uu + 4]) * inv, __uint_as_float(acc[cb + 8 * uu + 5]) * inv);
-              const uint32_t w = pack_bf16x2(__uint_as_float(acc[cb + 8 * uu + 6]) * inv, __uint_as_float(acc[cb + 8 * uu + 7]) * inv);
-              const uint32_t dst = stage + (uint32_t)lane * 128u + (((uint32_t)uu ^ ((uint32_t)lane & 7u)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-            }
-          }
-          if (P.o_stage == 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&tmap_o, stage, cb, t.head0, tok_w, t.n);
-              bulk_commit_group();
-            }
-          } else {
-            __syncwarp();
-            const int wv = (a.hd - cb >= 64 ? 64 : a.hd - cb) >> 1;   // valid 32-bit words per row in this chunk
-            if (wv > 0) {
-              const int dq = 32 / wv, dr = 32 % wv;
-              int row = lane / wv, w = lane - row * wv;
-              while (row < 32) {
-                const int rt = tok_w + (row >> P.pack_shift);
-                if (rt < a.Tq) {
-                  const uint32_t src = stage + (uint32_t)row * 128u + ((((uint32_t)w >> 2) ^ ((uint32_t)row & 7u)) << 4) +
-                                       (((uint32_t)w & 3u) << 2);
-                  uint32_t val;
-                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val) : "r"(src) : "memory");
-                  uint32_t* orow = reinterpret_cast<uint32_t*>(a.o + (long long)t.n * a.os_n + (long long)rt * a.os_t +
-                                                               (long long)(t.head0 + (row & (P.pack - 1))) * a.os_h + cb);
-                  orow[w] = val;
-                }
-                w += dr;
-                row += dq;
-                if (w >= wv) {
-                  w -= wv;
-                  ++row;
-                }
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
-      (void)head;
+      if (r == 0 && half == 0) trace(0x230u + (f & 15u));
     }
   }
 
   // ---- teardown
-  if (P.o_stage == 1 && warp < 8 && lane == 0) bulk_wait_group0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) {
+  if (warp == 15) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

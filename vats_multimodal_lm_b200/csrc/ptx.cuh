@@ -56,11 +56,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a barrier that has not completed after ~3e10 SM cycles (about 15 s) is a protocol bug — trap (the
-// launch fails with an error) instead of hanging the GPU.  clock64() is a single 64-bit SM-local counter; an earlier
-// version used %globaltimer with a 4 s limit and produced false time-outs (a torn 64-bit read at a 2^32 ns wrap of
-// the low word is off by 4.29 s).  The limit is checked twice before trapping.  Must stay inlined: kernels that
-// use setmaxnreg cannot contain real calls (ptxas would then cap every warp at the smallest register budget).
 __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
@@ -74,14 +69,19 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+// Bounded wait.  A barrier that has not completed after ~2^31 polls (minutes) is a protocol bug: trap (the launch fails
+// with an error) instead of hanging the GPU.  Production builds keep the wait loop to a handful of instructions —
+// every kernel here inlines it at a dozen sites and their hot loops are instruction-fetch-bound (ncu: stall_no_inst
+// is the top stall reason of the softmax warps), so the diagnostic version (clock-based limit + printf of the barrier
+// state, ~45 SASS instructions per site) is only compiled with -DVATS_MBAR_DEBUG.  Must stay inlined: kernels that
+// use setmaxnreg cannot contain real calls (ptxas would then cap every warp at the smallest register budget).
 __device__ __forceinline__ long long clock64_volatile() {
   long long t;
   asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
   return t;
 }
+#if defined(VATS_MBAR_DEBUG)
 __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
-  // plain try_wait polls (the default hardware suspend window); an explicit 2 us suspend-time hint was measured to
-  // add micro-seconds to every dependency edge (warps showed up as "sleeping").  The clock is read every 1024 polls.
   long long t0 = 0;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -99,9 +99,30 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, ui
     }
   }
 }
+#else
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
+  (void)tag;
+  // try_wait suspends the thread for a hardware-defined window per poll: 2^28 polls are tens of seconds at least
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls == (1u << 28)) __trap();
+  }
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
+}
+// The same for roles with slack (producers waiting for a free slot, the epilogue waiting for an accumulator): sleep
+// between polls, so the poll loop does not take issue slots and instruction fetches away from the warps of the same
+// sub-partition that are on the critical path (ncu on the resident-K/V kernel: ~40 % of all executed instructions
+// were poll-loop instructions).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 100) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++polls == (1u << 26)) __trap();
+  }
 }
 
 // generic-proxy writes -> visible to the async proxy (TMA / UMMA reading smem)
@@ -134,6 +155,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -143,6 +143,25 @@ int encode_map(CUtensorMap* map, const void* ptr, int N, int T, int heads, int h
   return VATS_OK;
 }
 
+// O as rows of 32-bit words for the resident-K/V kernel's untiled stores: dims (H*hd/2, Tq, N), box (pack*hd/2,
+// 32/pack, 1), no swizzle — the warp's 32 (token, head) rows are 32/pack contiguous runs of pack*hd elements.
+int encode_rows_map(CUtensorMap* map, const void* ptr, int N, int T, int H, int hd, const int64_t s[3], int pack) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[3] = {(cuuint64_t)H * hd / 2, (cuuint64_t)T, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)s[1] * 2, (cuuint64_t)s[0] * 2};
+  if (T == 1 || strides[0] == 0) strides[0] = (cuuint64_t)H * hd * 2;
+  if (N == 1 || strides[1] == 0) strides[1] = strides[0] * (cuuint64_t)T;
+  const cuuint32_t box[3] = {(cuuint32_t)(pack * hd / 2), (cuuint32_t)(32 / pack), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+    return fail(VATS_ERR_CUDA, "cuTensorMapEncodeTiled (row store map) failed (CUresult %d)", (int)rc);
+  return VATS_OK;
+}
+
 int sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -584,7 +603,22 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.hd_pad = (A.hd + 15) / 16 * 16;
   P.regions = (P.hd_pad + 63) / 64;
   P.n_pad = (A.Tk + 15) / 16 * 16;
-  P.o_off = (P.n_pad / 2 + 15) / 16 * 16;
+  if (2 * P.n_pad + P.hd_pad <= 512) {   // one O accumulator behind the two S slots
+    P.o_shared = 1;
+    P.slot_cols = P.n_pad;
+    P.o_off = 2 * P.n_pad;
+  } else {                               // O inside each slot's consumed S columns
+    P.o_shared = 0;
+    P.slot_cols = vats::kMidSlotCols;
+    P.o_off = (P.n_pad / 2 + 15) / 16 * 16;
+  }
+  if (const char* e = getenv("VATS_PREFILL_MID_OSHARED")) {   // tuning knob: 0 = always the in-slot accumulator
+    if (atoi(e) == 0) {
+      P.o_shared = 0;
+      P.slot_cols = vats::kMidSlotCols;
+      P.o_off = (P.n_pad / 2 + 15) / 16 * 16;
+    }
+  }
   // pack the group's heads into the tile rows when their count is a power of two (TMA box {64, pack, 128 / pack})
   int pack = 1;
   if ((hpg & (hpg - 1)) == 0) pack = hpg > 32 ? 32 : hpg;
@@ -605,12 +639,18 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     };
     P.ldg_vec = (A.hd % 4 == 0 && al8(A.q, A.qs) && al8(A.k, A.ks) && al8(A.v, A.vs)) ? 2 : 1;
   }
-  P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;
+  P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;   // (3 is decided below, once o_bufs is known)
   P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
+  P.cols_a = (P.n_pad + 31) / 32 * 16;
   const long long q_bytes = 2LL * P.regions * vats::kMidQRegionBytes;
   const long long kv_stage = 2LL * P.regions * P.n_pad * 128;
-  const long long budget = 227LL * 1024 - 1024 - (long long)sizeof(vats::MidBarriers) - q_bytes - 8 * vats::kTcOStageBytes;
-  long long nkv = budget / kv_stage;
+  long long nkv = 0;
+  for (int bufs = 2; bufs >= 1 && nkv < 1; --bufs) {   // two staging tiles per epilogue warp when they fit
+    const long long budget = 227LL * 1024 - 1024 - (long long)sizeof(vats::MidBarriers) - q_bytes -
+                             4LL * bufs * vats::kTcOStageBytes;
+    nkv = budget / kv_stage;
+    P.o_bufs = bufs;
+  }
   if (nkv < 1) return -1;
   if (nkv > vats::kMidMaxKv) nkv = vats::kMidMaxKv;
   {
@@ -622,9 +662,11 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     if (nkv_env >= 1 && nkv_env < nkv) nkv = nkv_env;
   }
   P.nkv = (int)nkv;
-  const size_t smem = vats::mid_smem_bytes(P.regions, P.n_pad, P.nkv);
+  const size_t smem = vats::mid_smem_bytes(P.regions, P.n_pad, P.nkv, P.o_bufs);
   vats::tc_find_divisor((unsigned)A.G, P.div_g);
   vats::tc_find_divisor((unsigned)P.q_tiles, P.div_qt);
+  P.trace = g_trace;
+  P.trace_cap = g_trace_cap;
 
   CUtensorMap mq, mk, mv, mo;
   std::memset(&mq, 0, sizeof(mq));
@@ -637,18 +679,38 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks, P.n_pad)) != VATS_OK) return rc;
     if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs, P.n_pad)) != VATS_OK) return rc;
   }
+  {
+    // O dense within a token (head stride == hd) and pack*hd*2 a multiple of 16 bytes: the warp's rows are 32/pack
+    // 16-byte aligned runs — one untiled TMA store per warp instead of one tile store per 64 columns, and it also
+    // serves dense head dims TMA tiles cannot address (66, 60)
+    static int rows_env = -1;
+    if (rows_env < 0) {
+      const char* e = getenv("VATS_PREFILL_MID_ROWSTORE");  // tuning knob: 0 = tile stores / coalesced stores
+      rows_env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const bool rows_ok = rows_env && A.os[2] == A.hd && (pack * A.hd * 2) % 16 == 0 && pack * A.hd <= 512 &&
+                         (A.Tq == 1 || (A.os[1] * 2) % 16 == 0) && (A.N == 1 || (A.os[0] * 2) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 &&
+                         (size_t)32 * A.hd * 2 <= (size_t)P.o_bufs * vats::kTcOStageBytes;
+    if (rows_ok) P.o_stage = 3;
+  }
   if (P.o_stage == 1 && (rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32 >> P.pack_shift, pack)) != VATS_OK)
     return rc;
+  if (P.o_stage == 3 && (rc = encode_rows_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, pack)) != VATS_OK) return rc;
   int grid = sm_count();
   if (grid > P.num_items) grid = P.num_items;
-  static thread_local SmemAttrCache smem_set[2];
-  if (any_ldg) {
-    CUDA_TRY(ensure_dyn_smem(vats::prefill_mid_kernel<true>, smem, smem_set[1]));
-    vats::prefill_mid_kernel<true><<<(unsigned)grid, vats::kMidThreads, smem, st>>>(P, mq, mk, mv, mo);
-  } else {
-    CUDA_TRY(ensure_dyn_smem(vats::prefill_mid_kernel<false>, smem, smem_set[0]));
-    vats::prefill_mid_kernel<false><<<(unsigned)grid, vats::kMidThreads, smem, st>>>(P, mq, mk, mv, mo);
+  static thread_local SmemAttrCache smem_set[4];
+#define VATS_MID_LAUNCH(L, S, IDX)                                                                      \
+  {                                                                                                     \
+    CUDA_TRY(ensure_dyn_smem(vats::prefill_mid_kernel<L, S>, smem, smem_set[IDX]));                     \
+    vats::prefill_mid_kernel<L, S><<<(unsigned)grid, vats::kMidThreads, smem, st>>>(P, mq, mk, mv, mo); \
   }
+  if (any_ldg) {
+    if (P.simple_mask) VATS_MID_LAUNCH(true, true, 3) else VATS_MID_LAUNCH(true, false, 2)
+  } else {
+    if (P.simple_mask) VATS_MID_LAUNCH(false, true, 1) else VATS_MID_LAUNCH(false, false, 0)
+  }
+#undef VATS_MID_LAUNCH
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
   g_last_kernel = VATS_LAUNCHED_PREFILL_MID;
