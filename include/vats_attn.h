@@ -105,6 +105,28 @@ size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, in
                                          const int64_t v_strides[3],
                                          const void* q, const void* k, const void* v);
 
+/*
+ * Prefill with the multi-GPU output gather fused into the kernel's epilogue (units are sharded by
+ * batch x KV-head group, the only exchange is the gather of the outputs).  This rank computes its local block
+ * q [N, Tq, H, hd] x k/v [N, Tk, G, hd] and every finished O tile is written, while it is still in shared memory, into
+ * the gathered tensor [N_total, Tq, H_total, hd] of EVERY rank at (seq_offset + n, :, head_offset + h, :) — TMA tile
+ * stores to peer memory over NVLink.  No second pass over O, no collective kernel.
+ *   o_ranks[r]  device pointer of rank r's gathered tensor as mapped into THIS process (symmetric memory / CUDA IPC);
+ *               all of them share o_strides.  o_ranks[rank] is the local copy.
+ * The caller synchronises the ranks around the call: nobody may still read the previous contents when a peer starts
+ * writing, and the gathered tensor is complete on a rank once every rank's launch has finished (a barrier on the
+ * stream after the call).  Runs on the tcgen05 tile kernel; the output must be TMA-addressable (16-byte aligned base
+ * and strides, head_dim % 8 == 0), otherwise VATS_ERR_UNSUPPORTED (use vats_attn_prefill + a collective).
+ */
+int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* const* o_ranks, int world, int rank,
+                             int seq_offset, int head_offset, int N_total, int H_total,
+                             const uint8_t* q_valid, const uint8_t* k_valid,
+                             int N, int Tq, int Tk, int H, int G, int hd,
+                             const int64_t q_strides[3], const int64_t k_strides[3],
+                             const int64_t v_strides[3], const int64_t o_strides[3],
+                             float scale, int causal, int left, int right,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / _SIMT / _MID). Host only. */
 int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
                            const int64_t q_strides[3], const int64_t k_strides[3],

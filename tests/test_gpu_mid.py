@@ -83,6 +83,24 @@ def test_mid_module_layout_hd66_uses_tma_and_matches_dense():
     check_close(o_dense, oracle_prefill(q, k, v, scale, False, -1, -1), "hd66")
 
 
+def test_mid_cpasync_staging_without_workspace_matches_repack_route():
+    """A C-ABI caller that passes no scratch gets the in-kernel cp.async staging (kLdg instantiation); the op layer hands
+    over scratch and gets repack + TMA.  Both must agree bit for bit (same arithmetic) and with the oracle."""
+    for (N, T, H, G, hd) in [(3, 196, 8, 2, 66), (2, 150, 6, 2, 60), (2, 77, 4, 4, 66)]:
+        q, k, v = make_qkv(N, T, T, H, G, hd, seed=hd + T)
+        dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
+        scale = hd ** -0.5
+        o_ws = ops.gqa_swa_prefill(dq, dk, dv, None, None, scale, True, 50, 0, MID)
+        o_raw = torch.empty_like(o_ws)
+        s3 = lambda t: tuple(t.stride()[:3])
+        _ffi.prefill(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), o_raw.data_ptr(), None, None, N, T, T, H, G, hd,
+                     s3(dq), s3(dk), s3(dv), s3(o_raw), scale, True, 50, 0, torch.cuda.current_stream().cuda_stream, MID)
+        torch.cuda.synchronize()
+        assert _ffi.last_kernel() == "prefill_mid"
+        assert torch.equal(o_ws, o_raw)
+        check_close(o_raw, oracle_prefill(q, k, v, scale, True, 50, 0), f"cp.async staging hd={hd}")
+
+
 def test_mid_unnormalised_peaky_logits():
     N, T, H, G, hd = 2, 200, 4, 2, 64
     q, k, v = make_qkv(N, T, T, H, G, hd, seed=5, unit_norm=False)

@@ -31,7 +31,7 @@ def _worker(rank, world, port, results):
     try:
         ok = True
         for (B, T, H, G, hd, causal, left) in [(4, 300, 8, 2, 64, True, 100), (2, 700, 4, 2, 128, True, 256),
-                                               (6, 196, 4, 2, 72, False, -1)]:
+                                               (6, 196, 4, 2, 72, False, -1), (1, 900, 8, 2, 128, True, 300)]:
             g = torch.Generator().manual_seed(11)
             q = torch.nn.functional.normalize(torch.randn(B, T, H, hd, generator=g), dim=-1).bfloat16().to(dev)
             k = torch.nn.functional.normalize(torch.randn(B, T, G, hd, generator=g), dim=-1).bfloat16().to(dev)
@@ -49,7 +49,20 @@ def _worker(rank, world, port, results):
             pg = sharding.PeerGather(B, T, H, hd, torch.bfloat16, dev)
             for _ in range(2):   # twice: the buffer is reused across calls
                 peer = sharding.local_attention_gather(core, ql, kl, vl, B, H, G, chunks=3, causal=causal, peer=pg)
+            fused = None
+            if hd % 8 == 0:   # the fused gather needs a TMA-addressable output
+                fg = sharding.FusedGather(B, T, H, hd, G, dev)
+                for _ in range(2):
+                    fused = fg.run(ql, kl, vl, scale, causal, left, 0 if causal else -1).clone()
             torch.cuda.synchronize()
+            if fused is not None:
+                # same tile kernel, same per-unit arithmetic: bit-identical; (<= 256 keys: `full` ran on the resident-K/V
+                # kernel, the fused gather on the tile kernel — compare with the tolerance there)
+                same = torch.equal(fused, full) if T > 256 else torch.allclose(fused.float(), full.float(), atol=2e-2, rtol=0)
+                ok = ok and same
+                if not same:
+                    print(f"rank {rank}: fused gather mismatch for {(B, T, H, G, hd)}: "
+                          f"{(fused.float() - full.float()).abs().max().item():.3e}")
             # token-chunked pieces see a shorter key range: same mask, same tiles for the rows they own, but a
             # different tile count can change the summation order of the online softmax -> compare with a tolerance
             for name, t in (("plain", plain), ("chunked", chunked), ("peer", peer)):

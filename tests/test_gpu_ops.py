@@ -452,3 +452,39 @@ def test_prefill_prepare_matches_oracle_and_feeds_attention(N, T, H, G, hd, pos0
     torch.cuda.synchronize()
     ref = oracle_prefill(dq.cpu(), dk.cpu(), dv.cpu(), hd ** -0.5, True, 64, 0)
     check_close(o, ref, "attention after prefill_prepare")
+
+
+# ---- fused output gather (vats_attn_prefill_gather): several "ranks" emulated on one GPU — every launch stores its
+#      block of the gathered tensor into ALL copies (here: plain device buffers instead of peer mappings)
+@pytest.mark.parametrize("split", ["batch", "groups"])
+def test_prefill_gather_writes_every_copy(split):
+    N, T, H, G, hd = 4, 300, 8, 4, 64
+    q, k, v = make_qkv(N, T, T, H, G, hd, seed=91)
+    dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
+    scale, causal, left = hd ** -0.5, True, 120
+    full = ops.gqa_swa_prefill(dq, dk, dv, None, None, scale, causal, left, 0, TC)
+    world = 2
+    copies = [torch.full((N, T, H, hd), float("nan"), dtype=torch.bfloat16, device="cuda") for _ in range(world)]
+    ptrs = [c.data_ptr() for c in copies]
+    hpg = H // G
+    for rank in range(world):
+        if split == "batch":
+            b0, b1, g0, g1 = rank * 2, rank * 2 + 2, 0, G
+        else:
+            b0, b1, g0, g1 = 0, N, rank * 2, rank * 2 + 2
+        ql, kl, vl = dq[b0:b1, :, g0 * hpg:g1 * hpg], dk[b0:b1, :, g0:g1], dv[b0:b1, :, g0:g1]
+        ops.gqa_swa_prefill_gather(ql, kl, vl, copies[rank], ptrs, rank, b0, g0 * hpg, None, None, scale, causal, left, 0)
+        assert _ffi.last_kernel() == "prefill_tc"
+    torch.cuda.synchronize()
+    for c in copies:
+        assert torch.equal(c, full)
+
+
+def test_prefill_gather_rejects_unaddressable_output():
+    N, T, H, G, hd = 1, 200, 4, 2, 60       # dense hd 60: rows only 8-byte aligned -> no TMA tile stores
+    q, k, v = make_qkv(N, T, T, H, G, hd, seed=92)
+    out = torch.zeros(N, T, H, hd, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_ffi.VatsAttnError) as e:
+        ops.gqa_swa_prefill_gather(q.cuda(), k.cuda(), v.cuda(), out, [out.data_ptr()], 0, 0, 0, None, None, 0.1, True,
+                                   -1, 0)
+    assert e.value.code == 2

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "vats_attn_prefill_ex",
     "vats_attn_prefill_ws",
     "vats_attn_prefill_workspace_bytes",
+    "vats_attn_prefill_gather",
     "vats_attn_prefill_plan",
     "vats_attn_decode",
     "vats_attn_decode_workspace_bytes",
@@ -105,6 +106,9 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_prefill_ws.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp, sz, vp]
         lib.vats_attn_prefill_workspace_bytes.restype = sz
         lib.vats_attn_prefill_workspace_bytes.argtypes = [i, i, i, i, i, i, p3, p3, p3, vp, vp, vp]
+        lib.vats_attn_prefill_gather.restype = i
+        lib.vats_attn_prefill_gather.argtypes = [vp, vp, vp, ctypes.POINTER(vp), i, i, i, i, i, i, vp, vp, i, i, i, i, i, i,
+                                                 p3, p3, p3, p3, f, i, i, i, vp, sz, vp]
         lib.vats_attn_prefill_plan.restype = i
         lib.vats_attn_prefill_plan.argtypes = [i, i, i, i, i, i, p3, p3, p3, p3, vp, vp, vp]
         lib.vats_attn_decode.restype = i
@@ -169,6 +173,20 @@ def prefill(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, q_valid_ptr: Optiona
         q_ptr, k_ptr, v_ptr, o_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd,
         _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
         float(scale), int(bool(causal)), int(left), int(right), int(kernel), workspace_ptr, workspace_bytes, stream))
+
+
+def prefill_gather(q_ptr: int, k_ptr: int, v_ptr: int, o_rank_ptrs: Sequence[int], rank: int, seq_offset: int,
+                   head_offset: int, N_total: int, H_total: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int],
+                   N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides, o_strides,
+                   scale: float, causal: bool, left: int, right: int, stream: int,
+                   workspace_ptr: Optional[int] = None, workspace_bytes: int = 0) -> None:
+    """vats_attn_prefill_gather: local attention whose O tiles are stored into every rank's gathered output."""
+    world = len(o_rank_ptrs)
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in o_rank_ptrs])
+    _check(load().vats_attn_prefill_gather(
+        q_ptr, k_ptr, v_ptr, arr, world, int(rank), int(seq_offset), int(head_offset), int(N_total), int(H_total),
+        q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd, _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
+        float(scale), int(bool(causal)), int(left), int(right), workspace_ptr, workspace_bytes, stream))
 
 
 def prefill_workspace_bytes(N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides,

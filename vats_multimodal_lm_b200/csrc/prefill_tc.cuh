@@ -58,6 +58,17 @@ struct TcParams {
   unsigned long long* trace;  // debug: block 0 appends (tag, clock64) pairs here (NULL = off); [0] = count
   int trace_cap;
   int order_softmax; // 1: the two softmax warpgroups take turns in the exponential phase (staggers the ping-pong)
+  // fused output gather (vats_attn_prefill_gather): every staged O tile is stored into the gathered output of ALL
+  // ranks (peer memory over NVLink) instead of the local output only
+  int peers;         // 0 = plain launch (tmap_o); W = number of ranks whose gathered tensors receive the tiles
+  int peer_first;    // first destination (each rank starts elsewhere, so no copy is hit by all ranks at once)
+  int seq_off;       // this rank's first sequence / head inside the gathered [N_total, Tq, H_total, hd] tensor
+  int head_off;
+};
+
+constexpr int kTcMaxPeers = 8;
+struct TcPeerMaps {
+  CUtensorMap m[kTcMaxPeers];   // tensor maps of the gathered output on rank 0..W-1 (box {64, 1, 32, 1}, 128B swizzle)
 };
 
 struct TcSmemBarriers {
@@ -217,7 +228,7 @@ template <bool kLdg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                  const __grid_constant__ CUtensorMap tmap_o) {
+                  const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ TcPeerMaps peer_maps) {
   using namespace ptx;
   extern __shared__ unsigned char smem_raw[];
   const PrefillParams& a = P.a;
@@ -243,7 +254,8 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
       prefetch_tmap(&tmap_k);
       prefetch_tmap(&tmap_v);
     }
-    if (P.o_stage == 1) prefetch_tmap(&tmap_o);
+    if (P.o_stage == 1 && P.peers == 0) prefetch_tmap(&tmap_o);
+    for (int rk = 0; rk < P.peers; ++rk) prefetch_tmap(&peer_maps.m[rk]);
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bars->q_full[t]), 1);
       mbar_init(smem_u32(&bars->q_fixed[t]), 128);
@@ -743,7 +755,17 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && row_w < a.Tq) {
-              tma_store_4d(&tmap_o, stage, cb, head, row_w, n);
+              if (P.peers == 0) {
+                tma_store_4d(&tmap_o, stage, cb, head, row_w, n);
+              } else {
+                // the gather, fused: the tile goes to every rank's copy of the gathered output while it is still in
+                // shared memory — no second pass over O, no collective kernel, no SM taken from the attention
+                int rk = P.peer_first;
+                for (int i = 0; i < P.peers; ++i) {
+                  tma_store_4d(&peer_maps.m[rk], stage, cb, head + P.head_off, row_w, n + P.seq_off);
+                  if (++rk == P.peers) rk = 0;
+                }
+              }
               bulk_commit_group();
             }
           } else {

@@ -183,6 +183,9 @@ struct PrefillArgs {
   int causal, left, right;
   void* ws = nullptr;       // caller-owned scratch (vats_attn_prefill_workspace_bytes), may be NULL
   size_t ws_bytes = 0;
+  // fused output gather (vats_attn_prefill_gather): `o` is unused, tiles go to o_ranks[0..world)
+  void* const* o_ranks = nullptr;
+  int world = 0, rank = 0, seq_off = 0, head_off = 0, N_total = 0, H_total = 0;
 };
 
 int validate_prefill(const PrefillArgs& A) {
@@ -409,7 +412,9 @@ size_t tc_repack_offsets(const PrefillArgs& A, const TcPlan& pl, size_t off[4]) 
   return off[3];
 }
 
-int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
+int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st);
+
+int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st, bool mid = false) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("VATS_PREFILL_REPACK");  // tuning knob: 0 = stage inside the kernel instead
@@ -462,7 +467,7 @@ int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) 
     rc = fail(VATS_ERR_CUDA, "repack kernel launch failed");
   } else {
     TcPlan pl2{LoadMode::kTma, LoadMode::kTma, LoadMode::kTma};
-    rc = launch_tc(B, pl2, st);
+    rc = mid ? launch_mid(B, pl2, st) : launch_tc(B, pl2, st);
   }
   if (rc == VATS_OK) g_launches += 1;
   return rc;
@@ -489,7 +494,7 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     };
     P.ldg_vec = (A.hd % 4 == 0 && al8(A.q, A.qs) && al8(A.k, A.ks) && al8(A.v, A.vs)) ? 2 : 1;
   }
-  P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
+  P.o_vec16 = ((reinterpret_cast<uintptr_t>(A.world > 0 ? A.o_ranks[0] : A.o) & 15u) == 0 && A.os[0] % 8 == 0 && A.os[1] % 8 == 0 &&
                A.os[2] % 8 == 0 && A.hd % 8 == 0)
                   ? 1
                   : 0;
@@ -518,7 +523,7 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   // O leaves through per-warp staging tiles (32 KB of shared memory) whenever the K/V rings keep two slots each:
   // as TMA tile stores when O is TMA-addressable, else as coalesced 32-bit stores when its rows are 4-byte aligned.
   {
-    const LoadMode om = plan_load(A.o, A.hd, A.os);
+    const LoadMode om = plan_load(A.world > 0 ? A.o_ranks[0] : A.o, A.hd, A.os);
     static int o_env = -1;
     if (o_env < 0) {
       const char* e = getenv("VATS_PREFILL_O_STAGE");  // tuning knob: 0 = per-thread row stores only
@@ -547,7 +552,24 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks)) != VATS_OK) return rc;
     if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs)) != VATS_OK) return rc;
   }
-  if (P.o_stage == 1 && (rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32)) != VATS_OK) return rc;
+  vats::TcPeerMaps peer_maps;
+  std::memset(&peer_maps, 0, sizeof(peer_maps));
+  if (A.world > 0) {
+    if (P.o_stage != 1)
+      return fail(VATS_ERR_UNSUPPORTED, "fused gather needs a TMA-addressable output (16-byte aligned base and strides, "
+                                        "head_dim a multiple of 8) and room for the staging tiles");
+    for (int r = 0; r < A.world; ++r) {
+      if ((reinterpret_cast<uintptr_t>(A.o_ranks[r]) & 15u) != 0)
+        return fail(VATS_ERR_INVALID_ARGUMENT, "o_ranks[%d] is not 16-byte aligned", r);
+      if ((rc = encode_map(&peer_maps.m[r], A.o_ranks[r], A.N_total, A.Tq, A.H_total, A.hd, A.os, 32)) != VATS_OK) return rc;
+    }
+    P.peers = A.world;
+    P.peer_first = (A.rank + 1) % A.world;
+    P.seq_off = A.seq_off;
+    P.head_off = A.head_off;
+  } else if (P.o_stage == 1 && (rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32)) != VATS_OK) {
+    return rc;
+  }
 
   const long long ctas = (long long)A.N * A.G * P.pairs * P.q_blocks;
   if (ctas > 0x7fffffffLL) return fail(VATS_ERR_UNSUPPORTED, "grid too large");
@@ -565,9 +587,9 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   else
     CUDA_TRY(ensure_dyn_smem(vats::prefill_tc_kernel<false>, smem, smem_set[0]));
   if (any_ldg)
-    vats::prefill_tc_kernel<true><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
+    vats::prefill_tc_kernel<true><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo, peer_maps);
   else
-    vats::prefill_tc_kernel<false><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
+    vats::prefill_tc_kernel<false><<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo, peer_maps);
   CUDA_TRY(cudaGetLastError());
   g_launches = 1;
   g_last_kernel = any_ldg ? VATS_LAUNCHED_PREFILL_TC_LDG : VATS_LAUNCHED_PREFILL_TC;
@@ -633,6 +655,13 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.tiles_per_item = (int)tpi;
   P.num_items = A.N * A.G;
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  if (any_ldg) {
+    // rows TMA cannot address (dense hd 66 / 60): with caller-owned scratch, one streaming repack + the TMA-fed
+    // kernel (cfg4a dense: 0.25 + 0.53 ms) beats the in-kernel cp.async staging (2.0 ms: 96 loader threads issuing
+    // 4-byte copies with per-copy address arithmetic)
+    const int rc2 = launch_tc_repacked(A, pl, st, /*mid=*/true);
+    if (rc2 >= 0) return rc2;
+  }
   {
     auto al8 = [&](const void* ptr, const int64_t* st3) {
       return (reinterpret_cast<uintptr_t>(ptr) & 7u) == 0 && st3[0] % 4 == 0 && st3[1] % 4 == 0 && st3[2] % 4 == 0;
@@ -946,6 +975,42 @@ int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o, c
   return prefill_impl(A, kernel, stream);
 }
 
+int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* const* o_ranks, int world, int rank,
+                             int seq_offset, int head_offset, int N_total, int H_total, const uint8_t* q_valid,
+                             const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
+                             const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                             const int64_t o_strides[3], float scale, int causal, int left, int right,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (!o_ranks || world < 1 || world > vats::kTcMaxPeers || rank < 0 || rank >= world)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "fused gather: need 1 <= world <= %d output pointers and 0 <= rank < world",
+                vats::kTcMaxPeers);
+  if (seq_offset < 0 || head_offset < 0 || seq_offset + N > N_total || head_offset + H > H_total)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "fused gather: the local [%d, %d] block at (%d, %d) does not fit the gathered "
+                "[%d, Tq, %d, hd] tensor", N, H, seq_offset, head_offset, N_total, H_total);
+  for (int r = 0; r < world; ++r)
+    if (!o_ranks[r]) return fail(VATS_ERR_INVALID_ARGUMENT, "fused gather: o_ranks[%d] is NULL", r);
+  PrefillArgs A{q, k, v, o_ranks[rank], q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
+                scale, causal, left, right};
+  A.ws = workspace;
+  A.ws_bytes = workspace ? workspace_bytes : 0;
+  A.o_ranks = o_ranks;
+  A.world = world;
+  A.rank = rank;
+  A.seq_off = seq_offset;
+  A.head_off = head_offset;
+  A.N_total = N_total;
+  A.H_total = H_total;
+  int rc = validate_prefill(A);
+  if (rc != VATS_OK) return rc;
+  if ((rc = check_device()) != VATS_OK) return rc;
+  if (N == 0 || Tq == 0) return VATS_OK;
+  TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
+  if (!tc_legal(A, &pl))
+    return fail(VATS_ERR_UNSUPPORTED, "fused gather runs on the tcgen05 tile kernel: geometry not supported (hd=%d)", hd);
+  return launch_tc(A, pl, reinterpret_cast<cudaStream_t>(stream));
+}
+
 size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, int hd, const int64_t q_strides[3],
                                          const int64_t k_strides[3], const int64_t v_strides[3], const void* q,
                                          const void* k, const void* v) {
@@ -955,7 +1020,8 @@ size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, in
   PrefillArgs A{q, k, v, nullptr, nullptr, nullptr, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, q_strides,
                 1.f, 0, -1, -1};
   TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
-  if (choose_kernel(A, &pl) != VATS_KERNEL_TCGEN05) return 0;
+  const int choice = choose_kernel(A, &pl);
+  if (choice != VATS_KERNEL_TCGEN05 && choice != VATS_KERNEL_MID) return 0;
   if (pl.q != LoadMode::kLdg && pl.k != LoadMode::kLdg && pl.v != LoadMode::kLdg) return 0;
   size_t off[4];
   return tc_repack_offsets(A, pl, off);

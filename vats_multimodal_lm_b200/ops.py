@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -93,6 +93,50 @@ def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: 
                      N, Tq, Tk, H, G, hd, qs, ks, vs, o.stride()[:3],
                      scale, causal, left, right, stream, kernel, ws.data_ptr() if ws is not None else None, ws_bytes)
     return o
+
+
+def gqa_swa_prefill_gather(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
+                           peer_ptrs: List[int], rank: int, seq_offset: int, head_offset: int,
+                           q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], scale: float, causal: bool,
+                           left: int, right: int) -> None:
+    """Local attention with the multi-GPU output gather fused into the kernel epilogue (vats_attn_prefill_gather).
+
+    q [N,Tq,H,hd], k/v [N,Tk,G,hd] are this rank's units; `out` is this rank's copy of the gathered
+    [N_total, Tq, H_total, hd] tensor and `peer_ptrs[r]` the device pointer of rank r's copy as mapped into this process
+    (`sharding.FusedGather` obtains them from symmetric memory).  Every O tile is written into all copies at
+    (seq_offset + n, :, head_offset + h, :).  Plain function (not a custom op): it writes peer memory, which the
+    dispatcher cannot describe; the caller brackets it with cross-rank barriers (see `sharding.FusedGather`)."""
+    _require_cuda_bf16("q", q)
+    _require_cuda_bf16("k", k)
+    _require_cuda_bf16("v", v)
+    _require_cuda_bf16("out", out)
+    if q.dim() != 4 or k.dim() != 4 or v.shape != k.shape or out.dim() != 4:
+        raise ValueError("q, k, v, out must be 4-D [N, T, heads, head_dim]")
+    N, Tq, H, hd = q.shape
+    Tk, G = k.size(1), k.size(2)
+    N_total, Tq_o, H_total, hd_o = out.shape
+    if Tq_o != Tq or hd_o != hd or k.size(0) != N or k.size(3) != hd or H % G != 0:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} out {tuple(out.shape)}")
+    if peer_ptrs[rank] != out.data_ptr():
+        raise ValueError("peer_ptrs[rank] must be the local gathered tensor")
+    q, k, v = _rowmajor_last(q), _rowmajor_last(k), _rowmajor_last(v)
+    qv = _valid_u8("q_valid", q_valid, N, Tq, q.device)
+    kv = _valid_u8("k_valid", k_valid, N, Tk, q.device)
+    if q.numel() == 0:
+        return
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        qs, ks, vs = q.stride()[:3], k.stride()[:3], v.stride()[:3]
+        ws, ws_bytes = None, 0
+        if hd % 8 != 0 or not _tma_strides(qs, ks, vs) or (q.data_ptr() | k.data_ptr() | v.data_ptr()) & 15:
+            ws_bytes = _ffi.prefill_workspace_bytes(N, Tq, Tk, H, G, hd, qs, ks, vs, q.data_ptr(), k.data_ptr(), v.data_ptr())
+            if ws_bytes:
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        _ffi.prefill_gather(q.data_ptr(), k.data_ptr(), v.data_ptr(), list(peer_ptrs), rank, seq_offset, head_offset,
+                            N_total, H_total, qv.data_ptr() if qv is not None else None,
+                            kv.data_ptr() if kv is not None else None, N, Tq, Tk, H, G, hd, qs, ks, vs,
+                            out.stride()[:3], scale, causal, left, right, stream,
+                            ws.data_ptr() if ws is not None else None, ws_bytes)
 
 
 def _tma_strides(*stride_sets) -> bool:

@@ -154,6 +154,44 @@ class PeerGather:
         return self.local
 
 
+class FusedGather:
+    """Attention + output gather in ONE kernel: the prefill kernel's epilogue stores every finished O tile into the
+    gathered [B, Tq, H, hd] tensor of every rank (TMA tile stores to peer memory over NVLink), so there is no second
+    pass over O, no collective kernel competing for SMs with the persistent attention kernel, and the transfer
+    overlaps the math tile by tile (`vats_attn_prefill_gather`).
+
+    The gathered tensor lives in symmetric memory (`torch.distributed._symmetric_memory`, one rendezvous per buffer;
+    reuse the object across calls).  `run` brackets the launch with the two device-side barriers the protocol needs:
+    nobody still reads the previous contents when the peers start writing; everybody's tiles have landed before
+    anybody reads.
+    """
+
+    def __init__(self, B: int, Tq: int, H: int, hd: int, G: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.B, self.H, self.G = B, H, G
+        self.shape = (B, Tq, H, hd)
+        self.local = symm_mem.empty(self.shape, dtype=torch.bfloat16, device=device)
+        self.handle = symm_mem.rendezvous(self.local, group=self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.shard = partition(B, G, self.world, self.rank)
+
+    def run(self, ql: torch.Tensor, kl: torch.Tensor, vl: torch.Tensor, scale: float, causal: bool, left: int,
+            right: int, q_valid: Optional[torch.Tensor] = None, k_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ql / kl / vl: this rank's units (`shard_qkv`).  Returns the gathered tensor (this rank's copy)."""
+        from . import ops
+        s = self.shard
+        hpg = self.H // self.G
+        self.handle.barrier()        # every rank is done with the previous contents
+        ops.gqa_swa_prefill_gather(ql, kl, vl, self.local, self.peer_ptrs, self.rank, s.b0, s.g0 * hpg, q_valid, k_valid,
+                                   scale, causal, left, right)
+        self.handle.barrier()        # every rank's tiles have landed everywhere
+        return self.local
+
+
 def local_attention_gather(core: Callable[..., torch.Tensor], ql: torch.Tensor, kl: torch.Tensor, vl: torch.Tensor,
                            B: int, H: int, G: int, *, q_valid: Optional[torch.Tensor] = None,
                            k_valid: Optional[torch.Tensor] = None, chunks: int = 1,
