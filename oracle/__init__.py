@@ -25,5 +25,5 @@ follows the flash-attn docstring / the intended contract and parity is "unpinned
 in DESIGN.md.
 """
 from .mask import mask_predicate  # noqa: F401
-from .sdpa import sdpa_explicit, decode_explicit, expand_kv  # noqa: F401
+from .sdpa import sdpa_explicit, sdpa_rows, decode_explicit, expand_kv  # noqa: F401
 from .prepare import decode_prepare_explicit, prefill_prepare_explicit, rope_tables  # noqa: F401

@@ -59,3 +59,34 @@ def decode_explicit(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tenso
         vb = v_cache[b:b + 1, lo:L]
         out[b] = sdpa_explicit(q[b:b + 1, None], kb, vb, None, scale, dtype)[0, 0]
     return out
+
+
+def sdpa_rows(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows: torch.Tensor, scale: float, causal: bool,
+              left: int, right: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Reference for a SAMPLE of query rows of one problem (used by bench.py to report max-abs / relative error at
+    full size, where the whole [Tq, Tk] score matrix would not fit): q [N,Tq,H,hd], k/v [N,Tk,G,hd] (CPU tensors),
+    `rows` int64 [R] query indices -> [N, R, H, hd].  Mask predicate of oracle/mask.py, bottom-right aligned; only the
+    key range the sampled rows can see is touched."""
+    N, Tq, H, hd = q.shape
+    Tk = k.size(1)
+    off = Tk - Tq
+    rows = rows.to(torch.int64)
+    i = rows[:, None] + off
+    lo = int(max(0, (rows.min().item() + off - left) if left >= 0 else 0))
+    hi = Tk - 1
+    if causal:
+        hi = min(hi, int(rows.max().item() + off))
+    if right >= 0:
+        hi = min(hi, int(rows.max().item() + off + right))
+    if hi < lo:
+        return torch.zeros(N, rows.numel(), H, hd, dtype=dtype)
+    j = torch.arange(lo, hi + 1, dtype=torch.int64)[None, :]
+    ok = torch.ones(rows.numel(), hi - lo + 1, dtype=torch.bool)
+    if causal:
+        ok &= j <= i
+    if left >= 0:
+        ok &= j >= i - left
+    if right >= 0:
+        ok &= j <= i + right
+    mask = ok[None].expand(N, -1, -1)
+    return sdpa_explicit(q[:, rows], k[:, lo:hi + 1], v[:, lo:hi + 1], mask, scale, dtype)
