@@ -127,6 +127,25 @@ int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* 
                              float scale, int causal, int left, int right,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Backward of vats_attn_prefill: the reference trains through the same modules
+ * (training/transformers/nlp/loops/training_loop.py:54-65) and torch differentiates its SDPA call
+ * (src/optimized_attention.py:709-714).  Given the forward inputs, the forward output o and dL/do:
+ *     dq [N, Tq, H, hd],  dk / dv [N, Tk, G, hd]   (DENSE bf16 outputs; dk / dv sum over the H/G heads of a group)
+ * Same mask predicate as the forward (rows / keys that are masked get zero gradient).  bf16 operands, fp32
+ * accumulation (mma.sync), deterministic.  workspace: vats_attn_prefill_backward_workspace_bytes(N, Tq, H) bytes of
+ * device scratch (the recomputed log-sum-exp and rowsum(do * o)); no zero-fill needed.
+ */
+int vats_attn_prefill_backward(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                               void* dq, void* dk, void* dv,
+                               const uint8_t* q_valid, const uint8_t* k_valid,
+                               int N, int Tq, int Tk, int H, int G, int hd,
+                               const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                               const int64_t o_strides[3], const int64_t do_strides[3],
+                               float scale, int causal, int left, int right,
+                               void* workspace, size_t workspace_bytes, void* stream);
+size_t vats_attn_prefill_backward_workspace_bytes(int N, int Tq, int H);
+
 /* Which kernel VATS_KERNEL_AUTO would pick for this geometry (VATS_KERNEL_TCGEN05 / _SIMT / _MID). Host only. */
 int vats_attn_prefill_plan(int N, int Tq, int Tk, int H, int G, int hd,
                            const int64_t q_strides[3], const int64_t k_strides[3],

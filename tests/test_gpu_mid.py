@@ -122,7 +122,7 @@ def test_mid_many_items_exercise_ring_wraparound():
 
 
 def test_auto_picks_mid_for_vit_shapes_and_kernels_agree():
-    N, T, H, G, hd = 6, 196, 16, 8, 72
+    N, T, H, G, hd = 10, 196, 16, 8, 72     # 80 (sequence, KV group) items: enough for AUTO to pick the kernel
     q, k, v = make_qkv(N, T, T, H, G, hd, seed=21)
     scale = hd ** -0.5
     o_auto = run_prefill(q, k, v, scale, False, -1, -1)

@@ -138,7 +138,7 @@ def test_two_kernels_agree_and_auto_plan():
     s = lambda t: t.stride()[:3]
     dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
     assert _ffi.prefill_plan(N, Tq, Tk, H, G, hd, s(dq), s(dk), s(dv), s(dq), dq.data_ptr(), dk.data_ptr(),
-                             dv.data_ptr()) == (ops.KERNEL_MID if Tk <= 256 else TC)
+                             dv.data_ptr()) == TC   # (N*G = 4 items: too few for the resident-K/V kernel)
     # ViT-3D temporal pass (8 tokens) and hd = 6 go to the CUDA-core kernel
     assert _ffi.prefill_plan(64, 8, 8, 32, 8, 66, (8 * 32 * 66, 32 * 66, 66), (8 * 8 * 66, 8 * 66, 66),
                              (8 * 8 * 66, 8 * 66, 66), (8 * 32 * 66, 32 * 66, 66), dq.data_ptr(), dk.data_ptr(),
@@ -409,7 +409,7 @@ def test_few_query_tokens_against_many_keys(N, Tq, Tk):
     s = lambda t: tuple(t.stride()[:3])
     dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
     assert _ffi.prefill_plan(N, Tq, Tk, H, G, hd, s(dq), s(dk), s(dv), s(dq), dq.data_ptr(), dk.data_ptr(),
-                             dv.data_ptr()) == (ops.KERNEL_MID if Tk <= 256 else TC)
+                             dv.data_ptr()) == TC   # (N*G = 4 items: too few for the resident-K/V kernel)
 
 
 # ---- fused prefill pre-core producers (qk-norm + RoPE + bf16 + TMA-addressable layout), SURVEY §8f rank 1

@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = (
     "vats_attn_prefill_ws",
     "vats_attn_prefill_workspace_bytes",
     "vats_attn_prefill_gather",
+    "vats_attn_prefill_backward",
+    "vats_attn_prefill_backward_workspace_bytes",
     "vats_attn_prefill_plan",
     "vats_attn_decode",
     "vats_attn_decode_workspace_bytes",
@@ -109,6 +111,11 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_prefill_gather.restype = i
         lib.vats_attn_prefill_gather.argtypes = [vp, vp, vp, ctypes.POINTER(vp), i, i, i, i, i, i, vp, vp, i, i, i, i, i, i,
                                                  p3, p3, p3, p3, f, i, i, i, vp, sz, vp]
+        lib.vats_attn_prefill_backward.restype = i
+        lib.vats_attn_prefill_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i,
+                                                   p3, p3, p3, p3, p3, f, i, i, i, vp, sz, vp]
+        lib.vats_attn_prefill_backward_workspace_bytes.restype = sz
+        lib.vats_attn_prefill_backward_workspace_bytes.argtypes = [i, i, i]
         lib.vats_attn_prefill_plan.restype = i
         lib.vats_attn_prefill_plan.argtypes = [i, i, i, i, i, i, p3, p3, p3, p3, vp, vp, vp]
         lib.vats_attn_decode.restype = i
@@ -187,6 +194,20 @@ def prefill_gather(q_ptr: int, k_ptr: int, v_ptr: int, o_rank_ptrs: Sequence[int
         q_ptr, k_ptr, v_ptr, arr, world, int(rank), int(seq_offset), int(head_offset), int(N_total), int(H_total),
         q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd, _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
         float(scale), int(bool(causal)), int(left), int(right), workspace_ptr, workspace_bytes, stream))
+
+
+def prefill_backward(q_ptr, k_ptr, v_ptr, o_ptr, do_ptr, dq_ptr, dk_ptr, dv_ptr, q_valid_ptr, k_valid_ptr,
+                     N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides, o_strides,
+                     do_strides, scale: float, causal: bool, left: int, right: int, workspace_ptr, workspace_bytes: int,
+                     stream: int) -> None:
+    _check(load().vats_attn_prefill_backward(
+        q_ptr, k_ptr, v_ptr, o_ptr, do_ptr, dq_ptr, dk_ptr, dv_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd,
+        _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides), _s3(do_strides), float(scale),
+        int(bool(causal)), int(left), int(right), workspace_ptr, workspace_bytes, stream))
+
+
+def prefill_backward_workspace_bytes(N: int, Tq: int, H: int) -> int:
+    return int(load().vats_attn_prefill_backward_workspace_bytes(N, Tq, H))
 
 
 def prefill_workspace_bytes(N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides,

@@ -1,0 +1,449 @@
+// backward.cuh — dQ / dK / dV of the GQA + sliding-window attention core.
+//
+// The reference trains through the same modules (training/transformers/nlp/loops/training_loop.py:54-65,
+// src/transformers/nlp/model.py:281-294 re-runs forward under `checkpoint`, tests/transformers/nlp/attention_tests.py
+// `test_gradients`), so the drop-in op needs a backward.  torch differentiates F.scaled_dot_product_attention
+// (src/optimized_attention.py:709-714) for the reference; here:
+//
+//   P = softmax(scale * Q K^T | mask)        D_i = sum_c dO_ic * O_ic
+//   dV = P^T dO        dP = dO V^T        dS = P o (dP - D)        dQ = scale * dS K        dK = scale * dS^T Q
+//   (GQA: dK / dV of a KV head sum over the H/G query heads that read it.)
+//
+// Two kernels, both bf16 operands / fp32 accumulation on mma.sync.m16n8k16 with operands staged in shared memory
+// (ldmatrix), deterministic (no atomics):
+//   attn_bwd_dq_kernel   one CTA per (sequence, query head, 64 query rows): recomputes the row statistics (the forward
+//                        kernels do not store a log-sum-exp), writes lse and D, then accumulates dQ over the KV blocks
+//                        the mask allows;
+//   attn_bwd_dkv_kernel  one CTA per (sequence, KV head, 64 keys): loops over the query heads of the group and the
+//                        query blocks, works on the TRANSPOSED tiles (S^T = K Q^T, so P^T / dS^T come out directly in
+//                        the fragment layout the dV / dK products need) and accumulates dK, dV.
+// The mask predicate is the one of mask.cuh (bit-exact with the forward kernels), including q_valid / k_valid and
+// fully masked rows (zero gradient).  This is a correct, tensor-core backward — not yet a tcgen05 one.
+#pragma once
+#include "decode_mma.cuh"   // ldmatrix / mma.sync wrappers
+#include "mask.cuh"
+#include "prefill_simt.cuh" // PrefillParams
+
+namespace vats {
+
+constexpr int kBwdThreads = 128;
+constexpr int kBwdBM = 64;   // query rows per block
+constexpr int kBwdBN = 64;   // keys per block
+
+struct BwdParams {
+  PrefillParams a;               // q, k, v, o (forward output), strides, mask, scale_log2
+  const __nv_bfloat16* dout;     // [N, Tq, H, hd], strides dos_*
+  long long dos_n, dos_t, dos_h;
+  __nv_bfloat16* dq;             // [N, Tq, H, hd] dense
+  __nv_bfloat16* dk;             // [N, Tk, G, hd] dense
+  __nv_bfloat16* dv;
+  float* lse;                    // [N, H, Tq] scaled-log2 log-sum-exp (+inf for rows without any allowed key)
+  float* dsum;                   // [N, H, Tq] D_i
+  float scale;
+  int hd_pad;                    // head dim rounded up to 16
+};
+
+__host__ __device__ inline size_t bwd_smem_bytes(int hd_pad) {
+  return (size_t)4 * kBwdBM * (hd_pad + 8) * 2 + 2 * kBwdBM * sizeof(float);
+}
+
+// rows [row0, row0 + 64) x hd of a row-strided bf16 matrix -> smem tile [64][pitch] (zero-filled past `rows` / hd)
+__device__ __forceinline__ void bwd_load_tile(__nv_bfloat16* dst, int pitch, const __nv_bfloat16* src, long long stride,
+                                              int row0, int rows, int hd, int hd_pad) {
+  const int wpr = hd_pad / 2;   // 32-bit words per staged row
+  for (int idx = threadIdx.x; idx < kBwdBM * wpr; idx += kBwdThreads) {
+    const int r = idx / wpr, w = idx - r * wpr;
+    uint32_t val = 0u;
+    if (row0 + r < rows && 2 * w < hd) val = *reinterpret_cast<const uint32_t*>(src + (long long)(row0 + r) * stride + 2 * w);
+    *reinterpret_cast<uint32_t*>(dst + r * pitch + 2 * w) = val;
+  }
+}
+
+// A fragment (16 x 16) of a row-major smem tile at (row0, k0)
+__device__ __forceinline__ void bwd_ldsm_a(const __nv_bfloat16* tile, int pitch, int row0, int k0, uint32_t (&a)[4]) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t addr = ptx::smem_u32(tile + (row0 + (lane & 15)) * pitch + k0 + (lane >> 4) * 8);
+  ldmatrix_x4(addr, a[0], a[1], a[2], a[3]);
+}
+// B fragments of two n-tiles (16 n x 16 k) from a tile stored [n][k]: (b[0], b[1]) = n-tile 0, (b[2], b[3]) = n-tile 1
+__device__ __forceinline__ void bwd_ldsm_b(const __nv_bfloat16* tile, int pitch, int n0, int k0, uint32_t (&b)[4]) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t addr = ptx::smem_u32(tile + (n0 + (lane & 7) + (lane >> 4) * 8) * pitch + k0 + ((lane >> 3) & 1) * 8);
+  ldmatrix_x4(addr, b[0], b[1], b[2], b[3]);
+}
+// ... from a tile stored [k][n] (transposed on the fly)
+__device__ __forceinline__ void bwd_ldsm_bt(const __nv_bfloat16* tile, int pitch, int k0, int n0, uint32_t (&b)[4]) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t addr = ptx::smem_u32(tile + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * pitch + n0 + (lane >> 4) * 8);
+  ldmatrix_x4_trans(addr, b[0], b[1], b[2], b[3]);
+}
+
+// key range [lo, hi] (inclusive, clamped to [0, Tk)) a query row may attend, geometry only; hi < lo = nothing
+__device__ __forceinline__ void bwd_row_range(const MaskParams& mp, int i, int* lo, int* hi) {
+  long long l = key_lo(mp, i), h = key_hi(mp, i);
+  if (l < 0) l = 0;
+  if (h > (long long)mp.Tk - 1) h = (long long)mp.Tk - 1;
+  *lo = l > 0x3fffffffLL ? 0x3fffffff : (int)l;
+  *hi = h < -1 ? -1 : (int)h;
+}
+
+// ---------------------------------------------------------------------------------------------------- dQ (+ lse, D)
+template <int KS>   // KS = hd_pad / 16
+__global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParams P) {
+  using namespace ptx;
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  const PrefillParams& a = P.a;
+  const int pitch = P.hd_pad + 8;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
+  __nv_bfloat16* sdO = sQ + kBwdBM * pitch;
+  __nv_bfloat16* sK = sdO + kBwdBM * pitch;
+  __nv_bfloat16* sV = sK + kBwdBM * pitch;
+  float* sD = reinterpret_cast<float*>(sV + kBwdBM * pitch);
+
+  const int q0 = blockIdx.x * kBwdBM, h = blockIdx.y, n = blockIdx.z;
+  const int g = h / a.hpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const __nv_bfloat16* qp = a.q + n * a.qs_n + (long long)h * a.qs_h;
+  const __nv_bfloat16* op = a.o + n * a.os_n + (long long)h * a.os_h;
+  const __nv_bfloat16* dop = P.dout + n * P.dos_n + (long long)h * P.dos_h;
+  const __nv_bfloat16* kp = a.k + n * a.ks_n + (long long)g * a.ks_h;
+  const __nv_bfloat16* vp = a.v + n * a.vs_n + (long long)g * a.vs_h;
+
+  // ---- Q, dO (and O, parked in the K buffer) -> smem;  D_i = sum_c dO_ic * O_ic
+  bwd_load_tile(sQ, pitch, qp, a.qs_t, q0, a.Tq, a.hd, P.hd_pad);
+  bwd_load_tile(sdO, pitch, dop, P.dos_t, q0, a.Tq, a.hd, P.hd_pad);
+  bwd_load_tile(sK, pitch, op, a.os_t, q0, a.Tq, a.hd, P.hd_pad);
+  __syncthreads();
+  {
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int c = half; c < P.hd_pad; c += 2) acc += __bfloat162float(sdO[r * pitch + c]) * __bfloat162float(sK[r * pitch + c]);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) sD[r] = acc;
+  }
+  __syncthreads();
+
+  // this thread's two rows: r0 = warp * 16 + gq, r1 = r0 + 8
+  const int rl0 = warp * 16 + gq, rl1 = rl0 + 8;
+  const int i0 = q0 + rl0, i1 = q0 + rl1;
+  int lo0 = 0, hi0 = -1, lo1 = 0, hi1 = -1;
+  if (i0 < a.Tq && (a.q_valid == nullptr || a.q_valid[(long long)n * a.Tq + i0])) bwd_row_range(a.mask, i0, &lo0, &hi0);
+  if (i1 < a.Tq && (a.q_valid == nullptr || a.q_valid[(long long)n * a.Tq + i1])) bwd_row_range(a.mask, i1, &lo1, &hi1);
+  const float D0 = sD[rl0], D1 = sD[rl1];
+
+  uint32_t qa[KS][4], da[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    bwd_ldsm_a(sQ, pitch, warp * 16, ks * 16, qa[ks]);
+    bwd_ldsm_a(sdO, pitch, warp * 16, ks * 16, da[ks]);
+  }
+
+  int t_first, t_last;
+  tile_range(a.mask, q0, kBwdBM, kBwdBN, &t_first, &t_last);
+
+  // S[16 x 64] of this warp for the KV block in sK, scaled to log2 units and masked (-inf)
+  auto scores = [&](int k0, float (&s)[8][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        bwd_ldsm_b(sK, pitch, np * 16, ks * 16, b);
+        mma_bf16_16816(s[np * 2], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[0], b[1]);
+        mma_bf16_16816(s[np * 2 + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = k0 + nt * 8 + tq * 2 + (e & 1);
+        const bool top = e < 2;
+        bool ok = top ? (j >= lo0 && j <= hi0) : (j >= lo1 && j <= hi1);
+        if (ok && a.k_valid != nullptr) ok = a.k_valid[(long long)n * a.Tk + j] != 0;
+        s[nt][e] = ok ? s[nt][e] * a.scale_log2 : -INFINITY;
+      }
+    }
+  };
+
+  // ---- pass 1: row statistics (online max / sum over the visited KV blocks)
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int t = t_first; t <= t_last; ++t) {
+    __syncthreads();
+    bwd_load_tile(sK, pitch, kp, a.ks_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
+    __syncthreads();
+    float s[8][4];
+    scores(t * kBwdBN, s);
+    float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      t0 = fmaxf(t0, fmaxf(s[nt][0], s[nt][1]));
+      t1 = fmaxf(t1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+    t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+    t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+    const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+    const float r0 = n0 == -INFINITY ? 0.f : n0, r1 = n1 == -INFINITY ? 0.f : n1;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      a0 += ex2(s[nt][0] - r0) + ex2(s[nt][1] - r0);
+      a1 += ex2(s[nt][2] - r1) + ex2(s[nt][3] - r1);
+    }
+    l0 = l0 * (m0 == -INFINITY ? 0.f : ex2(m0 - r0)) + a0;
+    l1 = l1 * (m1 == -INFINITY ? 0.f : ex2(m1 - r1)) + a1;
+    m0 = n0;
+    m1 = n1;
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // scaled-log2 log-sum-exp; rows without any allowed key get +inf, so that exp2(s - lse) = 0 everywhere
+  const float lse0 = (l0 > 0.f) ? m0 + __log2f(l0) : INFINITY;
+  const float lse1 = (l1 > 0.f) ? m1 + __log2f(l1) : INFINITY;
+  if (tq == 0) {
+    if (i0 < a.Tq) {
+      P.lse[((long long)n * a.H + h) * a.Tq + i0] = lse0;
+      P.dsum[((long long)n * a.H + h) * a.Tq + i0] = D0;
+    }
+    if (i1 < a.Tq) {
+      P.lse[((long long)n * a.H + h) * a.Tq + i1] = lse1;
+      P.dsum[((long long)n * a.H + h) * a.Tq + i1] = D1;
+    }
+  }
+
+  // ---- pass 2: dQ += (P o (dO V^T - D)) K
+  float dq[KS * 2][4];
+#pragma unroll
+  for (int nt = 0; nt < KS * 2; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+  for (int t = t_first; t <= t_last; ++t) {
+    __syncthreads();
+    bwd_load_tile(sK, pitch, kp, a.ks_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
+    bwd_load_tile(sV, pitch, vp, a.vs_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
+    __syncthreads();
+    float s[8][4];
+    scores(t * kBwdBN, s);
+    float dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        bwd_ldsm_b(sV, pitch, np * 16, ks * 16, b);
+        mma_bf16_16816(dp[np * 2], da[ks][0], da[ks][1], da[ks][2], da[ks][3], b[0], b[1]);
+        mma_bf16_16816(dp[np * 2 + 1], da[ks][0], da[ks][1], da[ks][2], da[ks][3], b[2], b[3]);
+      }
+    }
+    // dS in A-fragment form, one k-step (16 keys) per pair of n-tiles
+    uint32_t dsa[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int nt = 2 * j + u;
+        d[u][0] = ex2(s[nt][0] - lse0) * (dp[nt][0] - D0);
+        d[u][1] = ex2(s[nt][1] - lse0) * (dp[nt][1] - D0);
+        d[u][2] = ex2(s[nt][2] - lse1) * (dp[nt][2] - D1);
+        d[u][3] = ex2(s[nt][3] - lse1) * (dp[nt][3] - D1);
+      }
+      dsa[j][0] = pack_bf16x2(d[0][0], d[0][1]);
+      dsa[j][1] = pack_bf16x2(d[0][2], d[0][3]);
+      dsa[j][2] = pack_bf16x2(d[1][0], d[1][1]);
+      dsa[j][3] = pack_bf16x2(d[1][2], d[1][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int np = 0; np < KS; ++np) {
+        uint32_t b[4];
+        bwd_ldsm_bt(sK, pitch, j * 16, np * 16, b);
+        mma_bf16_16816(dq[np * 2], dsa[j][0], dsa[j][1], dsa[j][2], dsa[j][3], b[0], b[1]);
+        mma_bf16_16816(dq[np * 2 + 1], dsa[j][0], dsa[j][1], dsa[j][2], dsa[j][3], b[2], b[3]);
+      }
+    }
+  }
+  // ---- dQ * scale -> bf16 (dense [N, Tq, H, hd])
+  __nv_bfloat16* dqp = P.dq + (((long long)n * a.Tq) * a.H + h) * a.hd;
+#pragma unroll
+  for (int nt = 0; nt < KS * 2; ++nt) {
+    const int col = nt * 8 + tq * 2;
+    if (col < a.hd) {
+      if (i0 < a.Tq)
+        *reinterpret_cast<uint32_t*>(dqp + (long long)i0 * a.H * a.hd + col) = pack_bf16x2(dq[nt][0] * P.scale, dq[nt][1] * P.scale);
+      if (i1 < a.Tq)
+        *reinterpret_cast<uint32_t*>(dqp + (long long)i1 * a.H * a.hd + col) = pack_bf16x2(dq[nt][2] * P.scale, dq[nt][3] * P.scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- dK, dV
+template <int KS>
+__global__ void __launch_bounds__(kBwdThreads) attn_bwd_dkv_kernel(const BwdParams P) {
+  using namespace ptx;
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  const PrefillParams& a = P.a;
+  const int pitch = P.hd_pad + 8;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
+  __nv_bfloat16* sdO = sQ + kBwdBM * pitch;
+  __nv_bfloat16* sK = sdO + kBwdBM * pitch;
+  __nv_bfloat16* sV = sK + kBwdBM * pitch;
+  float* sLse = reinterpret_cast<float*>(sV + kBwdBM * pitch);
+  float* sD = sLse + kBwdBM;
+
+  const int k0 = blockIdx.x * kBwdBN, g = blockIdx.y, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const __nv_bfloat16* kp = a.k + n * a.ks_n + (long long)g * a.ks_h;
+  const __nv_bfloat16* vp = a.v + n * a.vs_n + (long long)g * a.vs_h;
+  bwd_load_tile(sK, pitch, kp, a.ks_t, k0, a.Tk, a.hd, P.hd_pad);
+  bwd_load_tile(sV, pitch, vp, a.vs_t, k0, a.Tk, a.hd, P.hd_pad);
+
+  // this thread's two key rows
+  const int j0 = k0 + warp * 16 + gq, j1 = j0 + 8;
+  const bool kv0 = j0 < a.Tk && (a.k_valid == nullptr || a.k_valid[(long long)n * a.Tk + j0]);
+  const bool kv1 = j1 < a.Tk && (a.k_valid == nullptr || a.k_valid[(long long)n * a.Tk + j1]);
+  const long long off = (long long)a.Tk - a.Tq;
+
+  float dk[KS * 2][4], dv[KS * 2][4];
+#pragma unroll
+  for (int nt = 0; nt < KS * 2; ++nt) {
+    dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+    dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f;
+  }
+
+  const int q_blocks = (a.Tq + kBwdBM - 1) / kBwdBM;
+  for (int hh = 0; hh < a.hpg; ++hh) {
+    const int h = g * a.hpg + hh;
+    const __nv_bfloat16* qp = a.q + n * a.qs_n + (long long)h * a.qs_h;
+    const __nv_bfloat16* dop = P.dout + n * P.dos_n + (long long)h * P.dos_h;
+    for (int qb = 0; qb < q_blocks; ++qb) {
+      const int q0 = qb * kBwdBM;
+      int t_first, t_last;
+      tile_range(a.mask, q0, kBwdBM, kBwdBN, &t_first, &t_last);
+      if ((int)blockIdx.x < t_first || (int)blockIdx.x > t_last) continue;   // no (query, key) pair of the two blocks is allowed
+      __syncthreads();
+      bwd_load_tile(sQ, pitch, qp, a.qs_t, q0, a.Tq, a.hd, P.hd_pad);
+      bwd_load_tile(sdO, pitch, dop, P.dos_t, q0, a.Tq, a.hd, P.hd_pad);
+      if (threadIdx.x < kBwdBM) {
+        const int i = q0 + threadIdx.x;
+        const bool live = i < a.Tq && (a.q_valid == nullptr || a.q_valid[(long long)n * a.Tq + i]);
+        sLse[threadIdx.x] = live ? P.lse[((long long)n * a.H + h) * a.Tq + i] : INFINITY;
+        sD[threadIdx.x] = live ? P.dsum[((long long)n * a.H + h) * a.Tq + i] : 0.f;
+      }
+      __syncthreads();
+
+      // ---- S^T = K Q^T for this warp's 16 keys x 64 queries, then P^T (rows = keys j0 / j1, columns = queries)
+      float st[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ka[4];
+        bwd_ldsm_a(sK, pitch, warp * 16, ks * 16, ka);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bq[4];
+          bwd_ldsm_b(sQ, pitch, np * 16, ks * 16, bq);
+          mma_bf16_16816(st[np * 2], ka[0], ka[1], ka[2], ka[3], bq[0], bq[1]);
+          mma_bf16_16816(st[np * 2 + 1], ka[0], ka[1], ka[2], ka[3], bq[2], bq[3]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int il = nt * 8 + tq * 2 + (e & 1);      // query column within the block
+          const long long ii = (long long)(q0 + il) + off;
+          const int j = e < 2 ? j0 : j1;
+          bool ok = e < 2 ? kv0 : kv1;
+          if (a.mask.causal && (long long)j > ii) ok = false;
+          if (a.mask.left >= 0 && (long long)j < ii - a.mask.left) ok = false;
+          if (a.mask.right >= 0 && (long long)j > ii + a.mask.right) ok = false;
+          st[nt][e] = ok ? ex2(st[nt][e] * a.scale_log2 - sLse[il]) : 0.f;   // lse = +inf for dead / padded rows
+        }
+      }
+      // ---- dV += P^T dO  (P^T straight into A-fragment form; contraction over the 64 queries)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(st[2 * jj][0], st[2 * jj][1]);
+        pa[1] = pack_bf16x2(st[2 * jj][2], st[2 * jj][3]);
+        pa[2] = pack_bf16x2(st[2 * jj + 1][0], st[2 * jj + 1][1]);
+        pa[3] = pack_bf16x2(st[2 * jj + 1][2], st[2 * jj + 1][3]);
+#pragma unroll
+        for (int np = 0; np < KS; ++np) {
+          uint32_t bd[4];
+          bwd_ldsm_bt(sdO, pitch, jj * 16, np * 16, bd);
+          mma_bf16_16816(dv[np * 2], pa[0], pa[1], pa[2], pa[3], bd[0], bd[1]);
+          mma_bf16_16816(dv[np * 2 + 1], pa[0], pa[1], pa[2], pa[3], bd[2], bd[3]);
+        }
+      }
+      // ---- dP^T = V dO^T,  dS^T = P^T o (dP^T - D)
+      float dpt[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t va[4];
+        bwd_ldsm_a(sV, pitch, warp * 16, ks * 16, va);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bd[4];
+          bwd_ldsm_b(sdO, pitch, np * 16, ks * 16, bd);
+          mma_bf16_16816(dpt[np * 2], va[0], va[1], va[2], va[3], bd[0], bd[1]);
+          mma_bf16_16816(dpt[np * 2 + 1], va[0], va[1], va[2], va[3], bd[2], bd[3]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int il = nt * 8 + tq * 2 + (e & 1);
+          st[nt][e] *= dpt[nt][e] - sD[il];
+        }
+      }
+      // ---- dK += dS^T Q
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t dsa[4];
+        dsa[0] = pack_bf16x2(st[2 * jj][0], st[2 * jj][1]);
+        dsa[1] = pack_bf16x2(st[2 * jj][2], st[2 * jj][3]);
+        dsa[2] = pack_bf16x2(st[2 * jj + 1][0], st[2 * jj + 1][1]);
+        dsa[3] = pack_bf16x2(st[2 * jj + 1][2], st[2 * jj + 1][3]);
+#pragma unroll
+        for (int np = 0; np < KS; ++np) {
+          uint32_t bq[4];
+          bwd_ldsm_bt(sQ, pitch, jj * 16, np * 16, bq);
+          mma_bf16_16816(dk[np * 2], dsa[0], dsa[1], dsa[2], dsa[3], bq[0], bq[1]);
+          mma_bf16_16816(dk[np * 2 + 1], dsa[0], dsa[1], dsa[2], dsa[3], bq[2], bq[3]);
+        }
+      }
+    }
+  }
+  // ---- bf16 outputs (dense [N, Tk, G, hd])
+  __nv_bfloat16* dkp = P.dk + (((long long)n * a.Tk) * a.G + g) * a.hd;
+  __nv_bfloat16* dvp = P.dv + (((long long)n * a.Tk) * a.G + g) * a.hd;
+#pragma unroll
+  for (int nt = 0; nt < KS * 2; ++nt) {
+    const int col = nt * 8 + tq * 2;
+    if (col < a.hd) {
+      if (j0 < a.Tk) {
+        *reinterpret_cast<uint32_t*>(dkp + (long long)j0 * a.G * a.hd + col) = pack_bf16x2(dk[nt][0] * P.scale, dk[nt][1] * P.scale);
+        *reinterpret_cast<uint32_t*>(dvp + (long long)j0 * a.G * a.hd + col) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+      }
+      if (j1 < a.Tk) {
+        *reinterpret_cast<uint32_t*>(dkp + (long long)j1 * a.G * a.hd + col) = pack_bf16x2(dk[nt][2] * P.scale, dk[nt][3] * P.scale);
+        *reinterpret_cast<uint32_t*>(dvp + (long long)j1 * a.G * a.hd + col) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+      }
+    }
+  }
+}
+
+}  // namespace vats

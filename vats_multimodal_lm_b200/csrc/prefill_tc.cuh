@@ -31,6 +31,15 @@
 
 namespace vats {
 
+// TMA producer lanes wait for a free ring slot most of the time: sleeping between polls (mbar_wait_relaxed) keeps their
+// poll loops off the issue ports of the softmax warps sharing the sub-partition.  -DVATS_TC_TIGHT_PRODUCERS restores the
+// plain poll loop for A/B measurements.
+#if defined(VATS_TC_TIGHT_PRODUCERS)
+#define VATS_TC_PRODUCER_WAIT(bar, parity) mbar_wait((bar), (parity))
+#else
+#define VATS_TC_PRODUCER_WAIT(bar, parity) mbar_wait_relaxed((bar), (parity), 64)
+#endif
+
 constexpr int kTcBlockM = 128;
 constexpr int kTcBlockN = 128;
 constexpr int kTcThreads = 384;
@@ -302,7 +311,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
               if (wk.n_tiles <= 0) continue;
               for (int t = 0; t < 2; ++t) {
                 if (t == 1 && !wk.active1) break;
-                mbar_wait(smem_u32(&bars->q_empty[t]), (qn[t] & 1u) ^ 1u);
+                VATS_TC_PRODUCER_WAIT(smem_u32(&bars->q_empty[t]), (qn[t] & 1u) ^ 1u);
                 const uint32_t bar = smem_u32(&bars->q_full[t]);
                 mbar_expect_tx(bar, tile_bytes);
                 for (int c = 0; c < P.regions; ++c)
@@ -326,7 +335,7 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
             const TcWork wk = tc_decode_work(P, w);
             for (int j = 0; j < wk.n_tiles; ++j) {
               const int k0 = (wk.t_first + j) * kTcBlockN;
-              mbar_wait(smem_u32(&empty[slot]), ph ^ 1u);
+              VATS_TC_PRODUCER_WAIT(smem_u32(&empty[slot]), ph ^ 1u);
               if (is_k) trace(0x310 + (j & 15));
               const uint32_t bar = smem_u32(&full[slot]);
               mbar_expect_tx(bar, tile_bytes);

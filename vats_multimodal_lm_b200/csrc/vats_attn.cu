@@ -24,6 +24,7 @@
 #include "prefill_mid.cuh"
 #include "decode_prepare.cuh"
 #include "repack.cuh"
+#include "backward.cuh"
 
 namespace {
 
@@ -759,7 +760,9 @@ int choose_kernel(const PrefillArgs& A, TcPlan* pl) {
   if (A.Tk < 32 && A.Tq < 256) return VATS_KERNEL_SIMT;
   // At most 256 keys: the whole K / V of a (sequence, KV group) is one tile — the resident-K/V kernel (ViT spatial
   // passes, text encoders, cross-attention contexts, short prompts).
-  if (A.Tk <= 256 && mid_enabled() && mid_legal(A, *pl)) return VATS_KERNEL_MID;
+  // It parallelises over (sequence, KV group) items only: with fewer items than half the SMs (a batch-1 prompt: 8
+  // items) the tile kernel's finer items (head pairs x query blocks) win — cfg1 T=32: 0.029 vs 0.039 ms.
+  if (A.Tk <= 256 && (long long)A.N * A.G >= sm_count() / 2 && mid_enabled() && mid_legal(A, *pl)) return VATS_KERNEL_MID;
   return VATS_KERNEL_TCGEN05;
 }
 
@@ -1009,6 +1012,88 @@ int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* 
   if (!tc_legal(A, &pl))
     return fail(VATS_ERR_UNSUPPORTED, "fused gather runs on the tcgen05 tile kernel: geometry not supported (hd=%d)", hd);
   return launch_tc(A, pl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t vats_attn_prefill_backward_workspace_bytes(int N, int Tq, int H) {
+  if (N <= 0 || Tq <= 0 || H <= 0) return 0;
+  return (size_t)2 * N * H * Tq * sizeof(float);   // log-sum-exp and D = rowsum(dO o O), fp32 [N, H, Tq] each
+}
+
+int vats_attn_prefill_backward(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
+                               void* dk, void* dv, const uint8_t* q_valid, const uint8_t* k_valid, int N, int Tq, int Tk,
+                               int H, int G, int hd, const int64_t q_strides[3], const int64_t k_strides[3],
+                               const int64_t v_strides[3], const int64_t o_strides[3], const int64_t do_strides[3],
+                               float scale, int causal, int left, int right, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  g_launches = 0;
+  PrefillArgs A{q, k, v, const_cast<void*>(o), q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides,
+                o_strides, scale, causal, left, right};
+  int rc = validate_prefill(A);
+  if (rc != VATS_OK) return rc;
+  if (!do_strides) return fail(VATS_ERR_INVALID_ARGUMENT, "stride arrays must not be NULL");
+  if ((rc = check_device()) != VATS_OK) return rc;
+  if (N == 0 || (Tq == 0 && Tk == 0)) return VATS_OK;
+  if (!dq || !dk || !dv || (Tq > 0 && !dout)) return fail(VATS_ERR_INVALID_ARGUMENT, "dout / dq / dk / dv must not be NULL");
+  if (hd > 128 || hd % 2 != 0)
+    return fail(VATS_ERR_UNSUPPORTED, "backward supports even head_dim <= 128 (got %d)", hd);
+  {
+    auto al4 = [](const void* p, const int64_t* s3) {
+      return (reinterpret_cast<uintptr_t>(p) & 3u) == 0 && s3[0] % 2 == 0 && s3[1] % 2 == 0 && s3[2] % 2 == 0;
+    };
+    if (!al4(q, q_strides) || !al4(k, k_strides) || !al4(v, v_strides) || !al4(o, o_strides) || !al4(dout, do_strides) ||
+        (reinterpret_cast<uintptr_t>(dq) & 3u) || (reinterpret_cast<uintptr_t>(dk) & 3u) || (reinterpret_cast<uintptr_t>(dv) & 3u))
+      return fail(VATS_ERR_UNSUPPORTED, "backward needs 4-byte aligned rows (even strides, 4-byte aligned bases)");
+  }
+  const size_t need = vats_attn_prefill_backward_workspace_bytes(N, Tq, H);
+  if (Tq > 0 && (!workspace || workspace_bytes < need))
+    return fail(VATS_ERR_WORKSPACE, "backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  if (N > 65535 || H > 65535) return fail(VATS_ERR_UNSUPPORTED, "backward grid limit: N and H must be <= 65535");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  vats::BwdParams P;
+  std::memset(&P, 0, sizeof(P));
+  fill_common(P.a, A);
+  P.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
+  P.dos_n = do_strides[0]; P.dos_t = do_strides[1]; P.dos_h = do_strides[2];
+  P.dq = reinterpret_cast<__nv_bfloat16*>(dq);
+  P.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  P.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  P.lse = reinterpret_cast<float*>(workspace);
+  P.dsum = P.lse + (size_t)N * H * Tq;
+  P.scale = scale;
+  P.hd_pad = (hd + 15) / 16 * 16;
+  const size_t smem = vats::bwd_smem_bytes(P.hd_pad);
+  const int ks = P.hd_pad / 16;
+  const dim3 grid_q((Tq + vats::kBwdBM - 1) / vats::kBwdBM, H, N);
+  const dim3 grid_k((Tk + vats::kBwdBN - 1) / vats::kBwdBN, G, N);
+  if (Tk == 0) {   // nothing to attend: all gradients are zero
+    CUDA_TRY(cudaMemsetAsync(dq, 0, (size_t)N * Tq * H * hd * 2, st));
+    return VATS_OK;
+  }
+#define VATS_BWD_CASE(KS)                                                                                         \
+  case KS: {                                                                                                      \
+    static thread_local SmemAttrCache c1, c2;                                                                     \
+    CUDA_TRY(ensure_dyn_smem(vats::attn_bwd_dq_kernel<KS>, smem, c1));                                            \
+    CUDA_TRY(ensure_dyn_smem(vats::attn_bwd_dkv_kernel<KS>, smem, c2));                                           \
+    if (Tq > 0) vats::attn_bwd_dq_kernel<KS><<<grid_q, vats::kBwdThreads, smem, st>>>(P);                         \
+    vats::attn_bwd_dkv_kernel<KS><<<grid_k, vats::kBwdThreads, smem, st>>>(P);                                    \
+  } break;
+  switch (ks) {
+    VATS_BWD_CASE(1)
+    VATS_BWD_CASE(2)
+    VATS_BWD_CASE(3)
+    VATS_BWD_CASE(4)
+    VATS_BWD_CASE(5)
+    VATS_BWD_CASE(6)
+    VATS_BWD_CASE(7)
+    VATS_BWD_CASE(8)
+    default:
+      return fail(VATS_ERR_UNSUPPORTED, "backward: head_dim %d not supported", hd);
+  }
+#undef VATS_BWD_CASE
+  CUDA_TRY(cudaGetLastError());
+  g_launches = Tq > 0 ? 2 : 1;
+  g_last_kernel = VATS_LAUNCHED_BACKWARD;
+  return VATS_OK;
 }
 
 size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, int hd, const int64_t q_strides[3],

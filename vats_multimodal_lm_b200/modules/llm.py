@@ -357,7 +357,10 @@ class Attention(nn.Module):
             cache_out = {"k": k_all[:, past:past + 1].to(x.dtype), "v": v_all[:, past:past + 1].to(x.dtype)}
             return self.w_o(o.to(x.dtype).reshape(B, 1, self.d_model)), cache_out
 
-        fused = _on_gpu(x) and hd % 2 == 0 and q.dtype in (torch.float32, torch.bfloat16)
+        # (training: the fused producers have no backward — qk-norm / RoPE then run as differentiable PyTorch ops and the
+        #  core's own backward kernels take over, `vats::gqa_swa_prefill_bwd`)
+        fused = _on_gpu(x) and hd % 2 == 0 and q.dtype in (torch.float32, torch.bfloat16) and not (
+            torch.is_grad_enabled() and q.requires_grad)
         if fused:
             # qk-norm + RoPE (positions past .. past+T-1) + bf16 rounding + TMA-addressable layout in ONE launch
             # (reference :467-474 does this with ~12 elementwise passes); the results feed the op directly

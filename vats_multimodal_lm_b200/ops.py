@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_bwd", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -93,6 +93,59 @@ def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: 
                      N, Tq, Tk, H, G, hd, qs, ks, vs, o.stride()[:3],
                      scale, causal, left, right, stream, kernel, ws.data_ptr() if ws is not None else None, ws_bytes)
     return o
+
+
+@torch.library.custom_op("vats::gqa_swa_prefill_bwd", mutates_args=(), device_types="cuda")
+def gqa_swa_prefill_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, dout: torch.Tensor,
+                        q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], scale: float, causal: bool,
+                        left: int, right: int) -> List[torch.Tensor]:
+    """Backward of `vats::gqa_swa_prefill` (vats_attn_prefill_backward): forward inputs, forward output `o` and dL/do
+    -> [dq, dk, dv] (bf16, dense; dk / dv carry the G un-expanded KV heads, summed over the heads of each group)."""
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("dout", dout)):
+        _require_cuda_bf16(name, t)
+    N, Tq, H, hd = q.shape
+    Tk, G = k.size(1), k.size(2)
+    q, k, v, o, dout = (_rowmajor_last(t) for t in (q, k, v, o, dout))
+    qv = _valid_u8("q_valid", q_valid, N, Tq, q.device)
+    kv = _valid_u8("k_valid", k_valid, N, Tk, q.device)
+    dq = torch.empty((N, Tq, H, hd), dtype=torch.bfloat16, device=q.device)
+    dk = torch.empty((N, Tk, G, hd), dtype=torch.bfloat16, device=q.device)
+    dv = torch.empty((N, Tk, G, hd), dtype=torch.bfloat16, device=q.device)
+    if q.numel() == 0 or k.numel() == 0:
+        return [dq.zero_(), dk.zero_(), dv.zero_()]
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        nbytes = max(_ffi.prefill_backward_workspace_bytes(N, Tq, H), 16)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
+        _ffi.prefill_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), dq.data_ptr(),
+                              dk.data_ptr(), dv.data_ptr(), qv.data_ptr() if qv is not None else None,
+                              kv.data_ptr() if kv is not None else None, N, Tq, Tk, H, G, hd, q.stride()[:3],
+                              k.stride()[:3], v.stride()[:3], o.stride()[:3], dout.stride()[:3], scale, causal, left,
+                              right, ws.data_ptr(), ws.numel(), stream)
+    return [dq, dk, dv]
+
+
+@gqa_swa_prefill_bwd.register_fake
+def _(q, k, v, o, dout, q_valid, k_valid, scale, causal, left, right):
+    return [q.new_empty(q.shape, dtype=torch.bfloat16), k.new_empty(k.shape, dtype=torch.bfloat16),
+            v.new_empty(v.shape, dtype=torch.bfloat16)]
+
+
+def _prefill_setup_context(ctx, inputs, output):
+    q, k, v, q_valid, k_valid, scale, causal, left, right, _kernel = inputs
+    ctx.save_for_backward(q, k, v, output, q_valid, k_valid)
+    ctx.attn_args = (scale, causal, left, right)
+
+
+def _prefill_backward(ctx, dout):
+    q, k, v, o, q_valid, k_valid = ctx.saved_tensors
+    scale, causal, left, right = ctx.attn_args
+    dq, dk, dv = torch.ops.vats.gqa_swa_prefill_bwd(q, k, v, o, dout.contiguous(), q_valid, k_valid, scale, causal, left,
+                                                    right)
+    return dq, dk, dv, None, None, None, None, None, None, None
+
+
+gqa_swa_prefill.register_autograd(_prefill_backward, setup_context=_prefill_setup_context)
 
 
 def gqa_swa_prefill_gather(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
@@ -357,6 +410,7 @@ def _no_cpu(name):
 
 
 gqa_swa_prefill.register_kernel("cpu")(_no_cpu("gqa_swa_prefill"))
+gqa_swa_prefill_bwd.register_kernel("cpu")(_no_cpu("gqa_swa_prefill_bwd"))
 gqa_swa_decode.register_kernel("cpu")(_no_cpu("gqa_swa_decode"))
 decode_prepare.register_kernel("cpu")(_no_cpu("decode_prepare"))
 prefill_prepare.register_kernel("cpu")(_no_cpu("prefill_prepare"))
