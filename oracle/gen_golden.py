@@ -152,8 +152,63 @@ def cross_case(name, seed, d_model, H, B, Tq, Tk, pad):
     print(name, tuple(out.shape), len(calls), "sdpa call(s)")
 
 
+def site_case(name, kind, seed, build, run):
+    """A remaining attention call site of the reference (image-gen self-attention, text encoder, video-gen factorized
+    self- / cross-attention): the module is run unmodified and every SDPA call (inputs, mask, output) is kept — the
+    fixtures pin `vats_multimodal_lm_b200.sdpa_adapter.sdpa_drop_in` on the exact tensors those call sites produce."""
+    m = ref.site(kind)
+    torch.manual_seed(seed)
+    mod = build(m).eval()
+    with torch.no_grad(), ref.capture_sdpa(m) as calls:
+        out = run(mod)
+    torch.save({"kind": "site_" + kind, "sdpa_calls": _pack_calls(calls), "out": out},
+               os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), len(calls), "sdpa call(s)",
+          [(tuple(c["q"].shape), None if c["attn_mask"] is None else tuple(c["attn_mask"].shape), c["is_causal"]) for c in calls])
+
+
+def site_cases():
+    B = 2
+    pm = lambda T, seed: (torch.rand(B, T, generator=torch.Generator().manual_seed(seed)) > 0.3)
+
+    def keep_first(mask):
+        mask = mask.clone()
+        mask[:, 0] = True
+        return mask
+
+    # image-generation causal self-attention: key padding & causal triangle (materialised AND), and plain is_causal
+    site_case("site_imagegen_self_pad", "imagegen_self", 601,
+              lambda m: m.CausalSelfAttention(128, 4, 2, 10000.0, 32 ** -0.5, False, True, False, False),
+              lambda mod: mod(torch.randn(B, 64, 128), False, True, True, -1, -1, False, keep_first(pm(64, 1))))
+    site_case("site_imagegen_self_ntk", "imagegen_self", 602,
+              lambda m: m.CausalSelfAttention(192, 4, 4, 10000.0, 48 ** -0.5, False, False, False, True, 2.0),
+              lambda mod: mod(torch.randn(B, 36, 192), False, True, True, -1, -1, False, None))
+    # text encoder: bidirectional, key padding (an .expand() view)
+    site_case("site_text_encoder_pad", "text_encoder", 603,
+              lambda m: m.Attention(128, 4, 2, 10000.0, 32 ** -0.5, False, True),
+              lambda mod: mod(torch.randn(B, 50, 128), False, True, keep_first(pm(50, 2))))
+    site_case("site_text_encoder_mqa", "text_encoder", 604,
+              lambda m: m.Attention(128, 4, 1, 10000.0, 32 ** -0.5, False, True),
+              lambda mod: mod(torch.randn(B, 40, 128), True, True, None))
+    # video-generation factorized causal self-attention: query-row padding x causal triangle, spatial then temporal
+    site_case("site_videogen_self_pad", "videogen_self", 605,
+              lambda m: m.CausalFactorizedAttention(128, 4, 2, 10000.0, 32 ** -0.5, False, True, False, False),
+              lambda mod: mod(torch.randn(B, 4, 9, 128), False, True, True, -1, -1, False,
+                              torch.ones(B, 36, dtype=torch.bool) & (torch.rand(B, 36) > 0.2)))
+    site_case("site_videogen_self", "videogen_self", 606,
+              lambda m: m.CausalFactorizedAttention(128, 4, 2, 10000.0, 32 ** -0.5, False, True, False, False),
+              lambda mod: mod(torch.randn(B, 4, 9, 128), False, True, True, -1, -1, False, None))
+    # video-generation factorized cross-attention: text keys with key padding
+    site_case("site_videogen_cross_pad", "videogen_cross", 607,
+              lambda m: m.FactorizedCrossAttention(128, 4, 2, 32 ** -0.5, False),
+              lambda mod: mod(torch.randn(B, 4, 9, 128), torch.randn(B, 12, 128), False, True, keep_first(pm(12, 3))))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--sites" in sys.argv:
+        site_cases()
+        return
     cross_case("cross_hd16_pad", 501, 128, 8, 2, 150, 16, True)
     cross_case("cross_hd64", 502, 128, 2, 1, 40, 70, False)
     prepare_seq_case("prepareseq_hd60_t40", 403, 6, 2, 60, 10000.0, 40, 2)
@@ -177,6 +232,7 @@ def main():
     vit3d_case("vit3d_hd66", 301, 132, 2, 1, (4, 3, 3), 2, False)
     vit3d_case("vit3d_hd66_pad", 302, 132, 2, 1, (4, 3, 3), 2, True)
     vit3d_case("vit3d_hd60_grid", 303, 120, 2, 2, (2, 6, 6), 1, True)
+    site_cases()
 
 
 if __name__ == "__main__":

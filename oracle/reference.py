@@ -54,6 +54,18 @@ def imagegen_cross():
     return m
 
 
+def site(name: str):
+    """One of the remaining attention call sites of the reference by short name."""
+    _ensure_path()
+    import importlib
+    return importlib.import_module({
+        "imagegen_self": "src.autoregressive_image_gen.autoregressive_transformer.attention.optimized_attention",
+        "text_encoder": "src.autoregressive_image_gen.text_encoder.encoder_attention",
+        "videogen_self": "src.autoregressive_video_gen.autoregressive_transformer.attention.optimized_attention",
+        "videogen_cross": "src.autoregressive_video_gen.autoregressive_transformer.attention.cross_attention",
+    }[name])
+
+
 @contextlib.contextmanager
 def capture_sdpa(module) -> "contextlib.AbstractContextManager[List[Dict[str, Any]]]":
     """Record every `F.scaled_dot_product_attention` call the reference module makes: the tensors entering the

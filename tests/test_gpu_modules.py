@@ -234,3 +234,25 @@ def test_cross_attention_block_matches_reference_fixture(name):
     with torch.no_grad():
         out = blk(fx["x"].cuda(), fx["text"].cuda(), pm)
     _close(out.cpu(), fx["out"], f"cross block {name}")
+
+
+# ---- the remaining attention call sites: image-gen causal self-attention, text encoder, video-gen
+#      factorized self- / cross-attention keep their own classes; their SDPA call is rerouted by sdpa_adapter.  The
+#      fixtures hold the exact tensors / masks those unmodified modules hand to SDPA and what it returned.
+import os  # noqa: E402
+
+from conftest import GOLDEN  # noqa: E402
+from vats_multimodal_lm_b200 import _ffi, sdpa_adapter  # noqa: E402
+
+
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLDEN) if f.startswith("site_")))
+def test_sdpa_drop_in_on_reference_call_site_captures(fname):
+    fx = load_golden(fname)
+    for ci, c in enumerate(fx["sdpa_calls"]):
+        mask = None if c["attn_mask"] is None else c["attn_mask"].cuda()
+        out = sdpa_adapter.sdpa_drop_in(c["q"].cuda(), c["k"].cuda(), c["v"].cuda(), attn_mask=mask,
+                                        is_causal=c["is_causal"], scale=c["scale"])
+        assert _ffi.last_kernel().startswith("prefill")
+        ref = torch.nan_to_num(c["out"], nan=0.0)
+        assert out.shape == ref.shape and out.dtype == c["q"].dtype
+        check_close(out, ref, f"{fname} call {ci}")

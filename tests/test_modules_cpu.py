@@ -136,7 +136,7 @@ def test_vit3d_spatial_precore_matches_reference_capture(fname):
     # temporal pass producers, fed with the reference's own spatial output
     B = fx["x"].size(0)
     sp = call["out"].permute(0, 2, 1, 3).reshape(B * grid[0], -1, m.d_model).view(B, grid[0], -1, m.d_model)
-    q2, k2, v2 = m._setup_qkv(sp, False, True, grid, "temporal")
+    q2, k2, v2 = (t.reshape(-1, *t.shape[2:]) for t in m._setup_qkv(sp, False, True, grid, "temporal"))  # [B,S,T,..] views
     call2 = fx["sdpa_calls"][1]
     torch.testing.assert_close(q2, call2["q"].permute(0, 2, 1, 3), atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(k2, _unexpand(call2["k"], G), atol=1e-5, rtol=1e-4)

@@ -9,7 +9,9 @@ The reference's model files bind the attention classes by name at import
 (`from src.optimized_attention import AttentionBlock, KVCache`, src/transformers/nlp/model.py:12;
 vit_2d/model.py:12; vit_3d/model.py:12; autoregressive_*/.../model.py:12), so besides replacing the attributes of the
 defining modules `patch_reference` rebinds the same names in every already-imported reference module.
-`unpatch_reference()` restores the originals.
+The reference's other attention modules (image-gen causal self-attention, text encoder, video-gen factorized self- and
+cross-attention) keep their classes; `patch_reference` reroutes their one `F.scaled_dot_product_attention` call to the
+kernels (`sdpa_adapter.FunctionalShim`).  `unpatch_reference()` restores the originals.
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ import sys
 from typing import Dict, List, Tuple
 
 from . import modules as _m
+from . import sdpa_adapter as _sdpa
 
 # defining module of the reference -> {attribute: drop-in}
 _TARGETS = {
@@ -61,6 +64,16 @@ def patch_reference(strict: bool = False) -> Dict[str, List[str]]:
             _saved.append((mod, attr, orig))
             setattr(mod, attr, repl)
             done.setdefault(mod_name, []).append(attr)
+    # the remaining attention call sites keep their own classes; only their SDPA call is rerouted (sdpa_adapter.py)
+    for mod_name in _sdpa.SDPA_CALL_SITES:
+        try:
+            mod = importlib.import_module(mod_name)
+        except Exception:
+            if strict:
+                raise
+            continue
+        _sdpa.install(mod)
+        done.setdefault(mod_name, []).append("F.scaled_dot_product_attention")
     # names already bound elsewhere by `from ... import X`
     for name, mod in list(sys.modules.items()):
         if mod is None or not (name == "src" or name.startswith(("src.", "training.", "scripts.", "tests."))):
@@ -75,6 +88,7 @@ def patch_reference(strict: bool = False) -> Dict[str, List[str]]:
 
 
 def unpatch_reference() -> None:
+    _sdpa.uninstall()
     while _saved:
         mod, attr, orig = _saved.pop()
         setattr(mod, attr, orig)

@@ -18,6 +18,7 @@ from typing import Literal, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
 from .llm import RMSNorm
 
@@ -95,22 +96,36 @@ class SpatioTemporalAttention(nn.Module):
 
     def _setup_qkv(self, x: torch.Tensor, use_mqa: bool, use_qk_norm: bool, grid_shape: Tuple[int, int, int],
                    attn_mode: str) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Projections, qk-norm and RoPE of one pass.  spatial: q/k/v [B*T, S, heads, hd].  temporal: [B, S, T, heads, hd]
+        as PERMUTED VIEWS of tensors laid out [B, T, S, heads, hd] — the reference materialises
+        `x.transpose(1, 2).contiguous()` first (vit_3d/optimized_attention.py:474-479, a full extra read + write of
+        the activations); the projection is row-wise and qk-norm / RoPE are element-wise along T, so nothing here needs
+        the transposed copy, and the one pass that casts q/k/v to the kernels' bf16 layout (`_pass`) does the
+        transposition on the way."""
         B, T, S, _ = x.shape
+        H, G, hd = self.num_heads, self.query_groups, self.head_dim
         if attn_mode == "spatial":
             x = x.reshape(B * T, S, self.d_model)
-        elif attn_mode == "temporal":
-            x = x.transpose(1, 2).reshape(B * S, T, self.d_model)
-        else:
+            q, k, v = torch.split(self.w_qkv(x), [H * hd, G * hd, G * hd], dim=-1)
+            n, L = x.shape[:2]
+            q = q.view(n, L, H, hd)
+            k = k.view(n, L, G, hd)
+            v = v.view(n, L, G, hd)
+            if use_qk_norm:
+                q, k = apply_qk_norm(q, k)
+            return self.rope(q, grid_shape, attn_mode), self.rope(k, grid_shape, attn_mode), v
+        if attn_mode != "temporal":
             raise ValueError(f"attn_mode must be 'spatial' or 'temporal', got {attn_mode}")
-        H, G, hd = self.num_heads, self.query_groups, self.head_dim
-        q, k, v = torch.split(self.w_qkv(x), [H * hd, G * hd, G * hd], dim=-1)
-        n, L = x.shape[:2]
-        q = q.view(n, L, H, hd)
-        k = k.view(n, L, G, hd)
-        v = v.view(n, L, G, hd)
+        q, k, v = torch.split(self.w_qkv(x), [H * hd, G * hd, G * hd], dim=-1)   # [B, T, S, .]: no transposed copy of x
+        # sequence axis = T (dim 1); (S, heads) together play the role of the head axis for the element-wise producers
+        q = q.reshape(B, T, S * H, hd)
+        k = k.reshape(B, T, S * G, hd)
         if use_qk_norm:
             q, k = apply_qk_norm(q, k)
-        return self.rope(q, grid_shape, attn_mode), self.rope(k, grid_shape, attn_mode), v
+        q = self.rope(q, grid_shape, attn_mode)
+        k = self.rope(k, grid_shape, attn_mode)
+        return (q.view(B, T, S, H, hd).permute(0, 2, 1, 3, 4), k.view(B, T, S, G, hd).permute(0, 2, 1, 3, 4),
+                v.reshape(B, T, S, G, hd).permute(0, 2, 1, 3, 4))
 
     def _pass(self, x: torch.Tensor, use_mqa: bool, use_qk_norm: bool, grid_shape, window, padding_mask,
               attn_mode: str) -> torch.Tensor:
@@ -122,8 +137,18 @@ class SpatioTemporalAttention(nn.Module):
             k_valid = padding_mask.reshape(B * T, S) if attn_mode == "spatial" else padding_mask.reshape(-1, T)
             k_valid = k_valid.bool()
         left, right = window
-        o = attention_core(q, k, v, scale=1.0 / math.sqrt(self.head_dim), causal=False, left=left, right=right,
-                           k_valid=k_valid, out_dtype=x.dtype)
+        scale = 1.0 / math.sqrt(self.head_dim)
+        if attn_mode == "temporal":
+            # the bf16 cast writes the [B*S, T, heads, hd] layout the kernel reads: transposition fused into the cast
+            def cast_transposed(t5):
+                buf = torch.empty(t5.shape, dtype=torch.bfloat16, device=t5.device)   # contiguous [B, S, T, heads, hd]
+                buf.copy_(t5)
+                return buf.view(B * S, T, t5.size(3), self.head_dim)
+            o = ops.gqa_swa_prefill(cast_transposed(q), cast_transposed(k), cast_transposed(v), None, k_valid, scale,
+                                    False, int(left), int(right)).to(x.dtype)
+            return o.reshape(B * S, T, self.d_model)
+        o = attention_core(q, k, v, scale=scale, causal=False, left=left, right=right, k_valid=k_valid,
+                           out_dtype=x.dtype)
         return o.reshape(q.size(0), q.size(1), self.d_model)
 
     def forward(self, x: torch.Tensor, grid_size: Tuple[int, int, int], use_mqa: bool, use_qk_norm: bool,
