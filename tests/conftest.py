@@ -26,7 +26,7 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_files():
     """Module-level fixtures (reference module run + captured SDPA calls); the prepare_* fixtures are listed apart."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith(("prepare", "cross_")))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith(("prepare", "cross_", "site_")))
 
 
 def cross_golden_files():
