@@ -195,6 +195,24 @@ int vats_attn_prefill_prepare(const void* q_in, const void* k_in, const void* v_
                               int qk_norm, float eps, void* stream);
 
 /*
+ * The same for the ViT passes, with the rotation given as tables (SURVEY.md §8f rank 1, 2-D axial and 3-D RoPE; rank 2):
+ *     out[c] = xn[c] * cos_table[tok][c] + xn[partner[c]] * sin_table[tok][c]
+ * covers every rotary variant of the reference — vit_2d/optimized_attention.py:128-172 (blocks x1, x2, y1, y2),
+ * vit_3d/rope_3d.py:97-219 (interleaved pairs of the h / w blocks or of the t block; other columns cos = 1, sin = 0).
+ * q_in / k_in / v_in are logical [No, Ni, T, heads, hd] tensors with strides (outer, inner, token, head) — sequence
+ * n = no * Ni + ni — so the ViT-3D temporal pass reads its [B, T, S, heads, hd] projections in place (No = B, Ni = S)
+ * and writes dense sequences [No * Ni, T, heads, hd(+pad)]: the transposed copy of vit_3d/optimized_attention.py:474-479
+ * is never made.  cos_table / sin_table [T, hd] fp32 (sin signed), partner [hd] int32; all three NULL = no rotation.
+ */
+int vats_attn_prefill_prepare_table(const void* q_in, const void* k_in, const void* v_in, int in_dtype,
+                                    void* q_out, void* k_out, void* v_out,
+                                    const float* cos_table, const float* sin_table, const int32_t* partner,
+                                    int No, int Ni, int T, int H, int G, int hd,
+                                    const int64_t qin_strides[4], const int64_t kin_strides[4], const int64_t vin_strides[4],
+                                    const int64_t qout_strides[3], const int64_t kout_strides[3], const int64_t vout_strides[3],
+                                    int qk_norm, float eps, void* stream);
+
+/*
  * Pre-core step of one cached decode token, fused into one launch (decode part):
  *     q, k = F.normalize(q, eps), F.normalize(k, eps)     utils/attention_utils.py:80-102   (only if qk_norm != 0)
  *     q, k = rope(q), rope(k)  at position seq_lens[b]-1  src/optimized_attention.py:97-143 (interleaved pairs 2i, 2i+1;

@@ -25,8 +25,17 @@ def _close(out, ref, what):
     assert max_abs <= MOD_MAX_ABS and rel <= MOD_REL_L2, f"{what}: max_abs={max_abs:.3e} rel_l2={rel:.3e}"
 
 
+@pytest.mark.parametrize("inference", [True, False], ids=["no_grad_fused_producers", "grad_unfused_producers"])
 @pytest.mark.parametrize("fname", golden_files())
-def test_module_matches_reference_fixture(fname):
+def test_module_matches_reference_fixture(fname, inference):
+    """inference=True runs under torch.no_grad(): the fused producers (qk-norm + RoPE + bf16 + layout in one launch;
+    1-D, 2-D axial, 3-D spatial and the in-place temporal pass) feed the core.  inference=False keeps autograd on: the
+    producers run as differentiable PyTorch ops.  Both must reproduce the unmodified reference's output."""
+    with torch.set_grad_enabled(not inference):
+        _module_fixture_case(fname)
+
+
+def _module_fixture_case(fname):
     fx = load_golden(fname)
     dev = "cuda"
     if fx["kind"] == "llm":
@@ -256,3 +265,32 @@ def test_sdpa_drop_in_on_reference_call_site_captures(fname):
         ref = torch.nan_to_num(c["out"], nan=0.0)
         assert out.shape == ref.shape and out.dtype == c["q"].dtype
         check_close(out, ref, f"{fname} call {ci}")
+
+
+def test_prefill_prepare_table_matches_torch_and_reads_permuted_views():
+    """vats::prefill_prepare_table against the modules' own PyTorch producers: 2-D axial RoPE on [B,1,T,..] and the
+    ViT-3D temporal pass read through (b, s)-permuted views of a [B, T, S, heads, hd] tensor."""
+    from vats_multimodal_lm_b200 import ops
+    from vats_multimodal_lm_b200.modules._common import apply_qk_norm
+    torch.manual_seed(0)
+    r2 = vl.RoPE2D(72, 64, 16, 10000.0).cuda()
+    B, T, H, G, hd = 3, 16, 4, 2, 72
+    q, k, v = torch.randn(B, T, H, hd, device="cuda"), torch.randn(B, T, G, hd, device="cuda"), torch.randn(B, T, G, hd, device="cuda")
+    cos, sin, partner = r2.tables(T)
+    qo, ko, vo = ops.prefill_prepare_table_views(q[:, None], k[:, None], v[:, None], cos, sin, partner, True)
+    qn, kn = apply_qk_norm(q, k)
+    torch.testing.assert_close(qo.float(), r2(qn), atol=8e-3, rtol=8e-3)
+    torch.testing.assert_close(ko.float(), r2(kn), atol=8e-3, rtol=8e-3)
+    torch.testing.assert_close(vo.float(), v, atol=2e-2, rtol=8e-3)
+    assert qo.shape == (B, T, H, hd) and qo.stride(2) == 72
+    r3 = vl.RoPE3D(66, 10000.0, (2, 16, 16)).cuda()
+    B, Tt, S, H, G, hd = 2, 4, 9, 4, 2, 66
+    q5 = torch.randn(B, Tt, S, H, hd, device="cuda")
+    k5 = torch.randn(B, Tt, S, G, hd, device="cuda")
+    v5 = torch.randn(B, Tt, S, G, hd, device="cuda")
+    cos, sin, partner = r3.tables((Tt, 3, 3), "temporal")
+    qo, ko, vo = ops.prefill_prepare_table_views(*(t.permute(0, 2, 1, 3, 4) for t in (q5, k5, v5)), cos, sin, partner, False)
+    ref_q = r3(q5.permute(0, 2, 1, 3, 4).reshape(B * S, Tt, H, hd), (Tt, 3, 3), "temporal")
+    torch.testing.assert_close(qo.float(), ref_q, atol=2e-2, rtol=8e-3)
+    torch.testing.assert_close(vo.float(), v5.permute(0, 2, 1, 3, 4).reshape(B * S, Tt, G, hd), atol=2e-2, rtol=8e-3)
+    assert qo.shape == (B * S, Tt, H, hd) and qo.is_contiguous()      # <= 32 tokens: dense for the short-sequence kernel

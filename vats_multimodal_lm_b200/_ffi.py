@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "vats_attn_decode_workspace_bytes",
     "vats_attn_decode_prepare",
     "vats_attn_prefill_prepare",
+    "vats_attn_prefill_prepare_table",
     "vats_attn_last_launch_count",
     "vats_attn_last_kernel",
     "vats_attn_debug_mask",
@@ -58,6 +59,7 @@ _lock = threading.Lock()
 
 _i64x3 = ctypes.c_int64 * 3
 _i64x2 = ctypes.c_int64 * 2
+_i64x4 = ctypes.c_int64 * 4
 
 # ctypes stride arrays are immutable inputs: build each distinct one once (the same few geometries repeat every step)
 _s3_cache: dict = {}
@@ -128,6 +130,9 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_prefill_prepare.restype = i
         lib.vats_attn_prefill_prepare.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, p3, p3,
                                                   i, f, vp]
+        lib.vats_attn_prefill_prepare_table.restype = i
+        lib.vats_attn_prefill_prepare_table.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i,
+                                                        p3, p3, p3, p3, p3, p3, i, f, vp]
         lib.vats_attn_last_launch_count.restype = i
         lib.vats_attn_last_launch_count.argtypes = []
         lib.vats_attn_last_kernel.restype = i
@@ -255,6 +260,16 @@ def prefill_prepare(q_in_ptr: int, k_in_ptr: int, v_in_ptr: int, in_fp32: bool, 
     _check(load().vats_attn_prefill_prepare(
         q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_out_ptr, v_out_ptr, cos_ptr, sin_ptr, N, T, H, G,
         hd, pos0, _s3(qin_strides), _s3(kin_strides), _s3(vin_strides), _s3(qout_strides),
+        _s3(kout_strides), _s3(vout_strides), int(bool(qk_norm)), float(eps), stream))
+
+
+def prefill_prepare_table(q_in_ptr, k_in_ptr, v_in_ptr, in_fp32: bool, q_out_ptr, k_out_ptr, v_out_ptr, cos_ptr, sin_ptr,
+                          partner_ptr, No: int, Ni: int, T: int, H: int, G: int, hd: int, qin_strides, kin_strides,
+                          vin_strides, qout_strides, kout_strides, vout_strides, qk_norm: bool, eps: float,
+                          stream: int) -> None:
+    _check(load().vats_attn_prefill_prepare_table(
+        q_in_ptr, k_in_ptr, v_in_ptr, int(bool(in_fp32)), q_out_ptr, k_out_ptr, v_out_ptr, cos_ptr, sin_ptr, partner_ptr,
+        No, Ni, T, H, G, hd, _i64x4(*qin_strides), _i64x4(*kin_strides), _i64x4(*vin_strides), _s3(qout_strides),
         _s3(kout_strides), _s3(vout_strides), int(bool(qk_norm)), float(eps), stream))
 
 

@@ -209,3 +209,97 @@ __global__ void __launch_bounds__(kPrepareWarps * 32) prefill_prepare_kernel(con
 }
 
 }  // namespace vats
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The producers of the ViT passes (SURVEY §8f rank 1, 2-D axial and 3-D RoPE): every rotary variant of the reference
+// (vit_2d/optimized_attention.py:128-172 — four blocks (x1, x2, y1, y2); vit_3d/rope_3d.py:97-219 — interleaved pairs
+// inside the h / w blocks or the t block) is, per token and column,
+//        out[c] = xn[c] * cos[tok][c] + xn[partner[c]] * sin[tok][c]
+// with a fixed column permutation `partner` and signed per-token tables — so ONE kernel serves them all: L2-normalise
+// q and k, rotate by table, pass v through, round to bf16 once and write the kernels' layout (head stride rounded up to
+// 8).  Sequences are indexed as n = n_outer * Ni + n_inner with separate input strides, so the ViT-3D temporal pass reads
+// its [B, T, S, heads, hd] projections in place and writes [B*S, T, heads, hd]: the reference's
+// `x.transpose(1, 2).contiguous()` (vit_3d/optimized_attention.py:474-479) never happens (§8f rank 2).
+namespace vats {
+
+struct PrepareTableParams {
+  const void* q_in;   // logical [No, Ni, T, H, hd], strides (q_no, q_ni, q_t, q_h), hd contiguous (bf16 or fp32)
+  const void* k_in;   // [No, Ni, T, G, hd]
+  const void* v_in;
+  int in_fp32;
+  __nv_bfloat16* q_out;   // dense sequences [No * Ni, T, heads, hd_stride]: strides (qo_n, qo_t, qo_h)
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* v_out;
+  const float* cos_table;   // [T, hd]
+  const float* sin_table;   // [T, hd] (signed)
+  const int* partner;       // [hd]
+  int No, Ni, T, H, G, hd;
+  long long q_no, q_ni, q_t, q_h, k_no, k_ni, k_t, k_h, v_no, v_ni, v_t, v_h;
+  long long qo_n, qo_t, qo_h, ko_n, ko_t, ko_h, vo_n, vo_t, vo_h;
+  int qk_norm;
+  float eps;
+};
+
+constexpr int kPrepareTableMaxHd = 256;
+
+__global__ void __launch_bounds__(kPrepareWarps * 32) prefill_prepare_table_kernel(const PrepareTableParams p) {
+  __shared__ float rows[kPrepareWarps][kPrepareTableMaxHd];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_tok = p.H + 2 * p.G;
+  const long long total = (long long)p.No * p.Ni * p.T * rows_per_tok;
+  const long long warps = (long long)gridDim.x * kPrepareWarps;
+  float* row = rows[warp];
+  for (long long r = (long long)blockIdx.x * kPrepareWarps + warp; r < total; r += warps) {
+    const long long nt = r / rows_per_tok;
+    const int rr = (int)(r - nt * rows_per_tok);
+    const long long n = nt / p.T;
+    const int t = (int)(nt - n * p.T);
+    const long long no = n / p.Ni;
+    const int ni = (int)(n - no * p.Ni);
+    const void* src;
+    long long src_off;
+    __nv_bfloat16* dst;
+    bool rotate;
+    if (rr < p.H) {
+      src = p.q_in; src_off = no * p.q_no + (long long)ni * p.q_ni + (long long)t * p.q_t + (long long)rr * p.q_h;
+      dst = p.q_out + n * p.qo_n + (long long)t * p.qo_t + (long long)rr * p.qo_h;
+      rotate = true;
+    } else if (rr < p.H + p.G) {
+      const int g = rr - p.H;
+      src = p.k_in; src_off = no * p.k_no + (long long)ni * p.k_ni + (long long)t * p.k_t + (long long)g * p.k_h;
+      dst = p.k_out + n * p.ko_n + (long long)t * p.ko_t + (long long)g * p.ko_h;
+      rotate = true;
+    } else {
+      const int g = rr - p.H - p.G;
+      src = p.v_in; src_off = no * p.v_no + (long long)ni * p.v_ni + (long long)t * p.v_t + (long long)g * p.v_h;
+      dst = p.v_out + n * p.vo_n + (long long)t * p.vo_t + (long long)g * p.vo_h;
+      rotate = false;
+    }
+    float ss = 0.f;
+    for (int c = lane; c < p.hd; c += 32) {
+      const float x = prepare_load(src, src_off + c, p.in_fp32);
+      row[c] = x;
+      ss += x * x;
+    }
+    float scale = 1.f;
+    if (rotate && p.qk_norm) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      scale = 1.f / fmaxf(sqrtf(ss), p.eps);
+    }
+    __syncwarp();
+    const bool rope = rotate && p.cos_table != nullptr;
+    for (int c = lane; c < p.hd; c += 32) {
+      float x = row[c] * scale;
+      if (rope) {
+        const float y = row[p.partner[c]] * scale;
+        x = x * p.cos_table[(long long)t * p.hd + c] + y * p.sin_table[(long long)t * p.hd + c];
+      }
+      dst[c] = __float2bfloat16(x);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace vats
+

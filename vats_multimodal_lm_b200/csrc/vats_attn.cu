@@ -1179,6 +1179,56 @@ int vats_attn_prefill_prepare(const void* q_in, const void* k_in, const void* v_
   return VATS_OK;
 }
 
+int vats_attn_prefill_prepare_table(const void* q_in, const void* k_in, const void* v_in, int in_dtype, void* q_out,
+                                    void* k_out, void* v_out, const float* cos_table, const float* sin_table,
+                                    const int32_t* partner, int No, int Ni, int T, int H, int G, int hd,
+                                    const int64_t qin_strides[4], const int64_t kin_strides[4],
+                                    const int64_t vin_strides[4], const int64_t qout_strides[3],
+                                    const int64_t kout_strides[3], const int64_t vout_strides[3], int qk_norm, float eps,
+                                    void* stream) {
+  g_launches = 0;
+  if (No < 0 || Ni < 0 || T < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
+  if (H <= 0 || G <= 0 || hd <= 0) return fail(VATS_ERR_INVALID_ARGUMENT, "H, G, hd must be positive");
+  if (in_dtype != 0 && in_dtype != 1) return fail(VATS_ERR_INVALID_ARGUMENT, "in_dtype must be 0 (bf16) or 1 (fp32)");
+  if (!qin_strides || !kin_strides || !vin_strides || !qout_strides || !kout_strides || !vout_strides)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "stride arrays must not be NULL");
+  const bool any = cos_table || sin_table || partner;
+  if (any && !(cos_table && sin_table && partner))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "cos_table, sin_table and partner must all be given or all be NULL");
+  if (hd > vats::kPrepareTableMaxHd) return fail(VATS_ERR_UNSUPPORTED, "head_dim %d > 256 is not supported", hd);
+  if (!(eps >= 0.f)) return fail(VATS_ERR_INVALID_ARGUMENT, "eps must be >= 0");
+  int rc = check_device();
+  if (rc != VATS_OK) return rc;
+  if (No == 0 || Ni == 0 || T == 0) return VATS_OK;
+  if (!q_in || !k_in || !v_in || !q_out || !k_out || !v_out)
+    return fail(VATS_ERR_INVALID_ARGUMENT, "tensor pointers must not be NULL");
+  vats::PrepareTableParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.q_in = q_in; p.k_in = k_in; p.v_in = v_in; p.in_fp32 = in_dtype;
+  p.q_out = reinterpret_cast<__nv_bfloat16*>(q_out);
+  p.k_out = reinterpret_cast<__nv_bfloat16*>(k_out);
+  p.v_out = reinterpret_cast<__nv_bfloat16*>(v_out);
+  p.cos_table = cos_table; p.sin_table = sin_table; p.partner = partner;
+  p.No = No; p.Ni = Ni; p.T = T; p.H = H; p.G = G; p.hd = hd;
+  p.q_no = qin_strides[0]; p.q_ni = qin_strides[1]; p.q_t = qin_strides[2]; p.q_h = qin_strides[3];
+  p.k_no = kin_strides[0]; p.k_ni = kin_strides[1]; p.k_t = kin_strides[2]; p.k_h = kin_strides[3];
+  p.v_no = vin_strides[0]; p.v_ni = vin_strides[1]; p.v_t = vin_strides[2]; p.v_h = vin_strides[3];
+  p.qo_n = qout_strides[0]; p.qo_t = qout_strides[1]; p.qo_h = qout_strides[2];
+  p.ko_n = kout_strides[0]; p.ko_t = kout_strides[1]; p.ko_h = kout_strides[2];
+  p.vo_n = vout_strides[0]; p.vo_t = vout_strides[1]; p.vo_h = vout_strides[2];
+  p.qk_norm = qk_norm ? 1 : 0;
+  p.eps = eps;
+  const long long rows = (long long)No * Ni * T * (H + 2 * G);
+  long long blocks = (rows + vats::kPrepareWarps - 1) / vats::kPrepareWarps;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  vats::prefill_prepare_table_kernel<<<(unsigned)blocks, vats::kPrepareWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches = 1;
+  g_last_kernel = VATS_LAUNCHED_PREFILL_PREPARE;
+  return VATS_OK;
+}
+
 int vats_attn_decode_prepare(const void* q_in, const void* k_in, const void* v_in, int in_dtype, void* q_out,
                              void* k_cache, void* v_cache, const int32_t* seq_lens, const float* cos_table,
                              const float* sin_table, int B, int H, int G, int hd, int S_max,

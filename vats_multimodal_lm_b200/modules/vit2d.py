@@ -15,8 +15,9 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
-from .llm import RMSNorm
+from .llm import RMSNorm, _on_gpu
 
 
 class RoPE(nn.Module):
@@ -41,6 +42,26 @@ class RoPE(nn.Module):
         theta_x = gx.flatten()[:, None] * self.inv_freq  # [T, hd/4]
         theta_y = gy.flatten()[:, None] * self.inv_freq
         return theta_x, theta_y
+
+    def tables(self, T: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """The rotation of `forward` as (cos [T, hd], signed sin [T, hd], partner [hd]) for the fused producer
+        (`vats::prefill_prepare_table`): out[c] = x[c] * cos[t][c] + x[partner[c]] * sin[t][c]."""
+        key = (T, self.inv_freq.device)
+        cached = getattr(self, "_tables", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        grid = int(math.sqrt(T))
+        assert grid * grid == self.num_patches, (
+            f"pos_x_flat must have shape of {(self.num_patches, 1)}, got {(grid * grid, 1)}")
+        tx, ty = self._angles(grid)
+        tx, ty = tx.float(), ty.float()
+        fd = self.head_dim // 4
+        cos = torch.cat([torch.cos(tx), torch.cos(tx), torch.cos(ty), torch.cos(ty)], dim=1).contiguous()
+        sin = torch.cat([-torch.sin(tx), torch.sin(tx), -torch.sin(ty), torch.sin(ty)], dim=1).contiguous()
+        idx = torch.arange(fd, device=cos.device)
+        partner = torch.cat([idx + fd, idx, idx + 3 * fd, idx + 2 * fd]).to(torch.int32)
+        self._tables = (key, (cos, sin, partner))
+        return cos, sin, partner
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         assert x.dim() == 4, f"x must have 4 dimensions, got {x.dim()} dimensions."
@@ -110,9 +131,24 @@ class SpatialAttention(nn.Module):
         mode = self.window_mode or get_default_window_mode()
         if not self.use_windowed_attn or mode == "reference_sdpa":
             left_window, right_window = -1, -1  # reference :601-603 (and its SDPA path never windows)
+        scale = 1.0 / math.sqrt(self.head_dim)
+        if _on_gpu(x) and x.dim() == 3 and x.size(1) > 0 and x.dtype in (torch.float32, torch.bfloat16) and not (
+                torch.is_grad_enabled() and (x.requires_grad or self.o_proj.weight.requires_grad)):
+            # inference: qk-norm + 2-D RoPE + bf16 rounding + kernel layout in ONE launch straight from the projection's
+            # views (the PyTorch path below needs ~12 element-wise passes and a cast / pad copy)
+            B, T, _ = x.shape
+            H, G, hd = self.num_heads, self.query_groups, self.head_dim
+            if self.use_fused_proj:
+                q, k, v = torch.split(self.qkv_proj(x), [H * hd, G * hd, G * hd], dim=-1)
+            else:
+                q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+            cos, sin, partner = self.rope.tables(T)
+            q, k, v = ops.prefill_prepare_table_views(q.view(B, 1, T, H, hd), k.view(B, 1, T, G, hd), v.view(B, 1, T, G, hd),
+                                                      cos, sin, partner, bool(use_qk_norm))
+            o = ops.gqa_swa_prefill(q, k, v, None, None, scale, False, int(left_window), int(right_window)).to(x.dtype)
+            return self.o_proj(o.reshape(B, T, self.d_model))
         q, k, v = self._setup_qkv(x, use_mqa=use_mqa, use_qk_norm=use_qk_norm)
-        o = attention_core(q, k, v, scale=1.0 / math.sqrt(self.head_dim), causal=False, left=left_window,
-                           right=right_window, out_dtype=x.dtype)
+        o = attention_core(q, k, v, scale=scale, causal=False, left=left_window, right=right_window, out_dtype=x.dtype)
         return self.o_proj(o.reshape(x.size(0), x.size(1), self.d_model))
 
 

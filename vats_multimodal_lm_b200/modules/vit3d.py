@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from .. import ops
 from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
-from .llm import RMSNorm
+from .llm import RMSNorm, _on_gpu
 
 
 class RoPE3D(nn.Module):
@@ -57,6 +57,43 @@ class RoPE3D(nn.Module):
         a, b = blk[..., 0], blk[..., 1]
         rot = torch.stack([a * cos - b * sin, a * sin + b * cos], dim=-1).reshape(*x.shape[:-1], 2 * pairs)
         return torch.cat([x[..., :start], rot, x[..., end:]], dim=-1)
+
+    def tables(self, grid_shape: Tuple[int, int, int], attn_mode: str
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """The rotation of `forward` as (cos [L, hd], signed sin [L, hd], partner [hd]) for the fused producer: the
+        rotated blocks hold interleaved pairs (2i, 2i+1); every other column has cos = 1, sin = 0."""
+        key = (tuple(grid_shape), attn_mode, self.freqs_t.device)
+        cached = getattr(self, "_tables", {})
+        if key in cached:
+            return cached[key]
+        gt, gh, gw = grid_shape
+        dev, hd, dpa = self.freqs_t.device, self.head_dim, self.dim_per_axis
+        if attn_mode == "spatial":
+            hh, ww = torch.meshgrid(torch.arange(gh, device=dev), torch.arange(gw, device=dev), indexing="ij")
+            blocks = [(hh.flatten(), self.freqs_h, dpa), (ww.flatten(), self.freqs_w, 2 * dpa)]
+            L = gh * gw
+        elif attn_mode == "temporal":
+            blocks = [(torch.arange(gt, device=dev), self.freqs_t, 0)]
+            L = gt
+        else:
+            raise ValueError(f"attn_mode must be 'spatial' or 'temporal' got {attn_mode}")
+        cos = torch.ones(L, hd, dtype=torch.float32, device=dev)
+        sin = torch.zeros(L, hd, dtype=torch.float32, device=dev)
+        partner = torch.arange(hd, device=dev)
+        for pos, freqs, start in blocks:
+            ang = pos.to(torch.float32)[:, None] * freqs.float()[None]          # [L, pairs]
+            pairs = freqs.numel()
+            ev = start + 2 * torch.arange(pairs, device=dev)
+            cos[:, ev] = torch.cos(ang)
+            cos[:, ev + 1] = torch.cos(ang)
+            sin[:, ev] = -torch.sin(ang)
+            sin[:, ev + 1] = torch.sin(ang)
+            partner[ev] = ev + 1
+            partner[ev + 1] = ev
+        out = (cos.contiguous(), sin.contiguous(), partner.to(torch.int32))
+        cached[key] = out
+        self._tables = cached
+        return out
 
     def forward(self, x: torch.Tensor, grid_shape: Tuple[int, int, int], attn_mode: Literal["spatial", "temporal"]
                 ) -> torch.Tensor:
@@ -130,7 +167,6 @@ class SpatioTemporalAttention(nn.Module):
     def _pass(self, x: torch.Tensor, use_mqa: bool, use_qk_norm: bool, grid_shape, window, padding_mask,
               attn_mode: str) -> torch.Tensor:
         B, T, S, _ = x.shape
-        q, k, v = self._setup_qkv(x, use_mqa, use_qk_norm, grid_shape, attn_mode)
         k_valid = None
         if padding_mask is not None:
             # reference :264-277 — plain re-views of the [B, T*H*W] mask, key-padding semantics
@@ -138,6 +174,23 @@ class SpatioTemporalAttention(nn.Module):
             k_valid = k_valid.bool()
         left, right = window
         scale = 1.0 / math.sqrt(self.head_dim)
+        H, G, hd = self.num_heads, self.query_groups, self.head_dim
+        if _on_gpu(x) and x.dtype in (torch.float32, torch.bfloat16) and not (
+                torch.is_grad_enabled() and (x.requires_grad or self.w_o.weight.requires_grad)):
+            # inference: qk-norm + 3-D RoPE + bf16 rounding + kernel layout in ONE launch, reading the projection in place
+            # — for the temporal pass through (b, s)-permuted views, so neither the transposed copy of x nor a cast pass
+            # exists any more
+            q, k, v = torch.split(self.w_qkv(x), [H * hd, G * hd, G * hd], dim=-1)       # [B, T, S, .]
+            q5, k5, v5 = q.view(B, T, S, H, hd), k.view(B, T, S, G, hd), v.view(B, T, S, G, hd)
+            if attn_mode == "spatial":      # sequences (b, t), tokens s
+                pass
+            else:                           # sequences (b, s), tokens t
+                q5, k5, v5 = (t.permute(0, 2, 1, 3, 4) for t in (q5, k5, v5))
+            cos, sin, partner = self.rope.tables(grid_shape, attn_mode)
+            qk, kk, vk = ops.prefill_prepare_table_views(q5, k5, v5, cos, sin, partner, bool(use_qk_norm))
+            o = ops.gqa_swa_prefill(qk, kk, vk, None, k_valid, scale, False, int(left), int(right)).to(x.dtype)
+            return o.reshape(qk.size(0), qk.size(1), self.d_model)
+        q, k, v = self._setup_qkv(x, use_mqa, use_qk_norm, grid_shape, attn_mode)
         if attn_mode == "temporal":
             # the bf16 cast writes the [B*S, T, heads, hd] layout the kernel reads: transposition fused into the cast
             def cast_transposed(t5):

@@ -19,7 +19,7 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_bwd", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_bwd", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "prefill_prepare_table", "prefill_prepare_table_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
@@ -371,6 +371,63 @@ def _(q, k, v, cos, sin, pos0, qk_norm, eps):
     return [t.new_empty((*t.shape[:3], hp), dtype=torch.bfloat16) for t in (q, k, v)]
 
 
+@torch.library.custom_op("vats::prefill_prepare_table", mutates_args=(), device_types="cuda")
+def prefill_prepare_table(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: Optional[torch.Tensor],
+                          sin: Optional[torch.Tensor], partner: Optional[torch.Tensor], qk_norm: bool, eps: float
+                          ) -> List[torch.Tensor]:
+    """Fused pre-core producers with a table-driven rotation (2-D axial / 3-D RoPE of the ViTs, any variant):
+    out[c] = xn[c] * cos[tok][c] + xn[partner[c]] * sin[tok][c] after the optional qk L2-norm; v passes through; one
+    rounding to bf16, written in the kernels' layout.  q [No, Ni, T, H, hd], k / v [No, Ni, T, G, hd] (bf16 or fp32, ANY
+    strides with a contiguous head_dim — e.g. permuted views) -> three buffers [No*Ni, T, heads, hd_pad]
+    (slice `[..., :hd]`).  cos / sin [T, hd] fp32, partner [hd] int32, or all None."""
+    if q.dim() != 5 or k.dim() != 5 or v.shape != k.shape or q.shape[:3] != k.shape[:3] or q.size(4) != k.size(4):
+        raise ValueError("q must be [No,Ni,T,H,hd]; k and v must be [No,Ni,T,G,hd]")
+    if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("q, k, v must share one dtype, bf16 or fp32")
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("prefill_prepare_table needs CUDA tensors (no CPU fallback)")
+    No, Ni, T, H, hd = q.shape
+    G = k.size(3)
+    given = [t is not None for t in (cos, sin, partner)]
+    if any(given) and not all(given):
+        raise ValueError("cos, sin and partner must all be given or all be None")
+    if cos is not None:
+        if cos.dtype != torch.float32 or sin.dtype != torch.float32 or partner.dtype != torch.int32 or \
+                cos.shape != (T, hd) or sin.shape != (T, hd) or partner.shape != (hd,):
+            raise ValueError("cos / sin must be fp32 [T, hd] tables and partner an int32 [hd] permutation")
+        cos, sin, partner = cos.contiguous(), sin.contiguous(), partner.contiguous()
+    fix = lambda t: t if t.stride(-1) == 1 or t.size(-1) == 1 else t.contiguous()
+    q, k, v = fix(q), fix(k), fix(v)
+    hp = hd if (hd % 8 == 0 or T <= 32) else (hd + 7) // 8 * 8
+    bufs = [torch.empty((No * Ni, T, heads, hp), dtype=torch.bfloat16, device=q.device) for heads in (H, G, G)]
+    if q.numel() == 0:
+        return bufs
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _ffi.prefill_prepare_table(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.dtype == torch.float32, bufs[0].data_ptr(),
+                                   bufs[1].data_ptr(), bufs[2].data_ptr(), cos.data_ptr() if cos is not None else None,
+                                   sin.data_ptr() if sin is not None else None,
+                                   partner.data_ptr() if partner is not None else None, No, Ni, T, H, G, hd,
+                                   q.stride()[:4], k.stride()[:4], v.stride()[:4], bufs[0].stride()[:3],
+                                   bufs[1].stride()[:3], bufs[2].stride()[:3], qk_norm, eps, stream)
+    return bufs
+
+
+@prefill_prepare_table.register_fake
+def _(q, k, v, cos, sin, partner, qk_norm, eps):
+    hd, T = q.size(4), q.size(2)
+    hp = hd if (hd % 8 == 0 or T <= 32) else (hd + 7) // 8 * 8
+    n = q.size(0) * q.size(1)
+    return [t.new_empty((n, T, t.size(3), hp), dtype=torch.bfloat16) for t in (q, k, v)]
+
+
+def prefill_prepare_table_views(q, k, v, cos, sin, partner, qk_norm: bool, eps: float = 1e-6):
+    """`vats::prefill_prepare_table`, returning q', k', v' as [..., :hd] views of the padded buffers."""
+    hd = q.size(-1)
+    qb, kb, vb = prefill_prepare_table(q, k, v, cos, sin, partner, qk_norm, eps)
+    return qb[..., :hd], kb[..., :hd], vb[..., :hd]
+
+
 def prefill_prepare_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cos: Optional[torch.Tensor],
                           sin: Optional[torch.Tensor], pos0: int, qk_norm: bool, eps: float = 1e-6):
     """`vats::prefill_prepare`, returning q', k', v' as [..., :hd] views of the padded buffers (what `gqa_swa_prefill`
@@ -414,3 +471,4 @@ gqa_swa_prefill_bwd.register_kernel("cpu")(_no_cpu("gqa_swa_prefill_bwd"))
 gqa_swa_decode.register_kernel("cpu")(_no_cpu("gqa_swa_decode"))
 decode_prepare.register_kernel("cpu")(_no_cpu("decode_prepare"))
 prefill_prepare.register_kernel("cpu")(_no_cpu("prefill_prepare"))
+prefill_prepare_table.register_kernel("cpu")(_no_cpu("prefill_prepare_table"))
