@@ -92,6 +92,13 @@ int vats_attn_prefill_ex(const void* q, const void* k, const void* v, void* o,
  * elements and the TMA-fed kernel runs on the copies; vats_attn_prefill_workspace_bytes() says how much that takes
  * (0 = no scratch needed).  Without a workspace (NULL / too small — what vats_attn_prefill and _ex pass) the kernel
  * stages such rows itself with cp.async, which is slower.  The library never allocates device memory.
+ *
+ * logit_bound > 0 is a promise by the caller that |<q, k>| <= logit_bound for every (query, key) pair — true by
+ * construction behind the reference's qk-norm (utils/attention_utils.py:80-102: q and k are unit vectors, RoPE is a
+ * rotation; pass 1.0).  Softmax is shift-invariant, so the kernels then use the bound instead of the row maximum:
+ * no maximum pass, no cross-warpgroup exchange, no rescaling of the accumulator.  The result is the same softmax
+ * (exponent arguments stay within 2 * bound * scale of zero).  0 = unknown: exact row maxima.  A violated promise can
+ * overflow the exponentials — it is a contract, not a hint.
  */
 int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o,
                          const uint8_t* q_valid, const uint8_t* k_valid,
@@ -99,7 +106,7 @@ int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o,
                          const int64_t q_strides[3], const int64_t k_strides[3],
                          const int64_t v_strides[3], const int64_t o_strides[3],
                          float scale, int causal, int left, int right, int kernel,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         float logit_bound, void* workspace, size_t workspace_bytes, void* stream);
 size_t vats_attn_prefill_workspace_bytes(int N, int Tq, int Tk, int H, int G, int hd,
                                          const int64_t q_strides[3], const int64_t k_strides[3],
                                          const int64_t v_strides[3],
@@ -125,7 +132,7 @@ int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* 
                              const int64_t q_strides[3], const int64_t k_strides[3],
                              const int64_t v_strides[3], const int64_t o_strides[3],
                              float scale, int causal, int left, int right,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             float logit_bound, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Backward of vats_attn_prefill: the reference trains through the same modules

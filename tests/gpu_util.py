@@ -28,13 +28,13 @@ def check_close(out, ref, what=""):
 
 
 def run_prefill(q, k, v, scale, causal, left, right, q_valid=None, k_valid=None, kernel=ops.KERNEL_AUTO,
-                device="cuda"):
+                device="cuda", logit_bound=0.0):
     dq = q.to(device)
     dk = k.to(device)
     dv = v.to(device)
     qv = None if q_valid is None else q_valid.to(device)
     kv = None if k_valid is None else k_valid.to(device)
-    o = ops.gqa_swa_prefill(dq, dk, dv, qv, kv, scale, causal, left, right, kernel)
+    o = ops.gqa_swa_prefill(dq, dk, dv, qv, kv, scale, causal, left, right, kernel, logit_bound)
     torch.cuda.synchronize()
     return o
 

@@ -149,3 +149,27 @@ def test_mid_strided_views_of_fused_qkv():
     q, k, v = torch.split(qkv, [H * hd, G * hd, G * hd], dim=-1)
     ref = oracle_prefill(q.view(N, T, H, hd), k.view(N, T, G, hd), v.view(N, T, G, hd), 0.05, True, 90, 0)
     check_close(o, ref, "fused qkv views")
+
+
+@pytest.mark.parametrize("kernel", [MID, ops.KERNEL_TCGEN05], ids=["mid", "tcgen05"])
+@pytest.mark.parametrize("shape", [(3, 196, 196, 4, 2, 72), (2, 196, 196, 8, 2, 66), (2, 256, 256, 4, 2, 128),
+                                   (2, 77, 250, 4, 4, 64), (1, 700, 700, 4, 2, 64)], ids=lambda s: "x".join(map(str, s)))
+def test_bounded_logits_skip_the_row_maximum_and_give_the_same_softmax(shape, kernel):
+    """logit_bound = 1.0 is what the modules pass behind qk-norm (unit-norm q, k): the kernels use the bound instead of
+    the row maximum (softmax is shift-invariant).  Same results as the exact-maximum path, same oracle tolerance, for
+    every mask form incl. fully masked rows and key padding."""
+    N, Tq, Tk, H, G, hd = shape
+    if kernel == MID and Tk > 256:
+        pytest.skip("resident-K/V kernel: <= 256 keys")
+    q, k, v = make_qkv(N, Tq, Tk, H, G, hd, seed=sum(shape))      # unit-norm q, k
+    g = torch.Generator().manual_seed(5)
+    kv = torch.rand(N, Tk, generator=g) > 0.3
+    kv[:, 0] = True
+    scale = 1.0 / math.sqrt(hd)
+    for causal, left, right, use_kv in [(False, -1, -1, False), (True, 60, 0, False), (True, -1, 0, True), (False, 9, 30, True)]:
+        kvm = kv if use_kv else None
+        o_b = run_prefill(q, k, v, scale, causal, left, right, None, kvm, kernel=kernel, logit_bound=1.0)
+        o_e = run_prefill(q, k, v, scale, causal, left, right, None, kvm, kernel=kernel)
+        ref = oracle_prefill(q, k, v, scale, causal, left, right, None, kvm)
+        check_close(o_b, ref, f"bounded {shape} causal={causal} ({left},{right}) kv={use_kv}")
+        assert (o_b.float() - o_e.float()).abs().max().item() <= 1e-2

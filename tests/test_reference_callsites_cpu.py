@@ -51,7 +51,7 @@ def oracle_ops(monkeypatch):
     """Stand-ins for the four ops the LLM drop-in calls, computed by the CPU oracle (bf16-rounded like the kernels)."""
     log = OpLog()
 
-    def prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
+    def prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0, logit_bound=0.0):
         log.calls.append(("prefill", tuple(q.shape), tuple(k.shape)))
         m = mask_predicate(q.size(0), q.size(1), k.size(1), causal, left, right, q_valid, k_valid)
         return sdpa_explicit(q, k, v, m, scale).to(torch.bfloat16)

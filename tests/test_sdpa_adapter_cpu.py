@@ -18,7 +18,7 @@ REF = os.environ.get("VATS_REFERENCE", "/root/reference")
 
 @pytest.fixture()
 def oracle_op(monkeypatch):
-    def prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
+    def prefill(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0, logit_bound=0.0):
         m = mask_predicate(q.size(0), q.size(1), k.size(1), causal, left, right, q_valid, k_valid)
         return sdpa_explicit(q, k, v, m, scale).to(torch.bfloat16)
     monkeypatch.setattr(ops, "gqa_swa_prefill", prefill)

@@ -48,7 +48,8 @@ def main():
                 buf[..., :hd] = x
                 return buf[..., :hd]
             q, k, v = pad(q), pad(k), pad(v)
-        f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0)
+        bound = 1.0 if "--bound" in sys.argv else 0.0   # unit-norm q, k: what the modules pass behind qk-norm
+        f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, causal, left, 0 if causal else -1, 0, bound)
         for _ in range(reps):
             o = f()
         if "--time" in sys.argv:   # CUDA-event timing of 20 further calls (inputs > L2 or L2 flushed by the next call's data)

@@ -107,12 +107,12 @@ def load() -> ctypes.CDLL:
         lib.vats_attn_prefill_ex.restype = i
         lib.vats_attn_prefill_ex.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp]
         lib.vats_attn_prefill_ws.restype = i
-        lib.vats_attn_prefill_ws.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, vp, sz, vp]
+        lib.vats_attn_prefill_ws.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, p3, p3, p3, p3, f, i, i, i, i, f, vp, sz, vp]
         lib.vats_attn_prefill_workspace_bytes.restype = sz
         lib.vats_attn_prefill_workspace_bytes.argtypes = [i, i, i, i, i, i, p3, p3, p3, vp, vp, vp]
         lib.vats_attn_prefill_gather.restype = i
         lib.vats_attn_prefill_gather.argtypes = [vp, vp, vp, ctypes.POINTER(vp), i, i, i, i, i, i, vp, vp, i, i, i, i, i, i,
-                                                 p3, p3, p3, p3, f, i, i, i, vp, sz, vp]
+                                                 p3, p3, p3, p3, f, i, i, i, f, vp, sz, vp]
         lib.vats_attn_prefill_backward.restype = i
         lib.vats_attn_prefill_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i,
                                                    p3, p3, p3, p3, p3, f, i, i, i, vp, sz, vp]
@@ -179,26 +179,28 @@ def prefill(q_ptr: int, k_ptr: int, v_ptr: int, o_ptr: int, q_valid_ptr: Optiona
             N: int, Tq: int, Tk: int, H: int, G: int, hd: int,
             q_strides: Sequence[int], k_strides: Sequence[int], v_strides: Sequence[int], o_strides: Sequence[int],
             scale: float, causal: bool, left: int, right: int, stream: int, kernel: int = KERNEL_AUTO,
-            workspace_ptr: Optional[int] = None, workspace_bytes: int = 0) -> None:
+            workspace_ptr: Optional[int] = None, workspace_bytes: int = 0, logit_bound: float = 0.0) -> None:
     lib = load()
     _check(lib.vats_attn_prefill_ws(
         q_ptr, k_ptr, v_ptr, o_ptr, q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd,
         _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
-        float(scale), int(bool(causal)), int(left), int(right), int(kernel), workspace_ptr, workspace_bytes, stream))
+        float(scale), int(bool(causal)), int(left), int(right), int(kernel), float(logit_bound), workspace_ptr,
+        workspace_bytes, stream))
 
 
 def prefill_gather(q_ptr: int, k_ptr: int, v_ptr: int, o_rank_ptrs: Sequence[int], rank: int, seq_offset: int,
                    head_offset: int, N_total: int, H_total: int, q_valid_ptr: Optional[int], k_valid_ptr: Optional[int],
                    N: int, Tq: int, Tk: int, H: int, G: int, hd: int, q_strides, k_strides, v_strides, o_strides,
                    scale: float, causal: bool, left: int, right: int, stream: int,
-                   workspace_ptr: Optional[int] = None, workspace_bytes: int = 0) -> None:
+                   workspace_ptr: Optional[int] = None, workspace_bytes: int = 0, logit_bound: float = 0.0) -> None:
     """vats_attn_prefill_gather: local attention whose O tiles are stored into every rank's gathered output."""
     world = len(o_rank_ptrs)
     arr = (ctypes.c_void_p * world)(*[int(p) for p in o_rank_ptrs])
     _check(load().vats_attn_prefill_gather(
         q_ptr, k_ptr, v_ptr, arr, world, int(rank), int(seq_offset), int(head_offset), int(N_total), int(H_total),
         q_valid_ptr, k_valid_ptr, N, Tq, Tk, H, G, hd, _s3(q_strides), _s3(k_strides), _s3(v_strides), _s3(o_strides),
-        float(scale), int(bool(causal)), int(left), int(right), workspace_ptr, workspace_bytes, stream))
+        float(scale), int(bool(causal)), int(left), int(right), float(logit_bound), workspace_ptr, workspace_bytes,
+        stream))
 
 
 def prefill_backward(q_ptr, k_ptr, v_ptr, o_ptr, do_ptr, dq_ptr, dk_ptr, dv_ptr, q_valid_ptr, k_valid_ptr,

@@ -55,6 +55,11 @@ struct MidParams {
   int o_shared;        // 1: ONE O accumulator behind both S slots (2 * n_pad + hd_pad <= 512): a slot is free for the
                        //    next S as soon as its P was consumed; 0: O lives inside each slot's consumed S columns
   int o_off;           // TMEM column of O: absolute (o_shared) or relative to the slot
+  int pb_col;          // TMEM column (relative to the slot) where warpgroup B writes its half of P: its OWN S columns
+                       // (cols_a) when O is shared — no ordering against A's reads needed — else right behind A's P
+  int bounded;         // 1: the caller guarantees |q.k| <= logit bound (qk-norm): the row maximum is not computed,
+                       //    p = exp2(s * scale_log2 - bound_log2) — softmax is shift-invariant, so the result is the same
+  float bound_log2;    // logit bound * scale * log2(e)
   int o_bufs;          // staging tiles per epilogue warp (2 = the TMA read of one chunk overlaps staging the next)
   int pack, pack_shift;  // query heads packed into one tile (power of two <= 32), its log2
   int tok_per_tile;    // 128 >> pack_shift
@@ -420,8 +425,10 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
           const uint32_t tD = P.o_shared ? tmem_u + (uint32_t)P.o_off : tP + (uint32_t)P.o_off;
           const uint32_t v_lo = v_lo_base + (uint32_t)vs * kv_step;
           uint32_t acc = 0u;
+          const int ksteps_a = P.cols_a / 16;   // k-steps whose P comes from warpgroup A's columns
           for (int k = 0; k < ksteps_o; ++k) {
-            mma_ts_lohi(tD, tP + (uint32_t)k * 8u, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc, leader);
+            const uint32_t pcol = k < ksteps_a ? (uint32_t)k * 8u : (uint32_t)P.pb_col + (uint32_t)(k - ksteps_a) * 8u;
+            mma_ts_lohi(tD, tP + pcol, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc, leader);
             acc = 1u;
           }
           tc_commit_pred(smem_u32(&bars->o_full[s]), leader);
@@ -699,50 +706,76 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         }
         tmem_ld_wait();
         if (r == 0 && half == 0) trace(0x280u + (f & 15u));
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g * 16 < my_n) {
-            const int cg = my_c0 + g * 16;
-            if (kSimple) {
-              if (cg + 16 > a.Tk) {   // the group that holds the end of the sequence (warp-uniform)
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (cg + i >= a.Tk) v[g * 16 + i] = 0xff800000u;
+        if (!P.bounded) {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  #pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 16 < my_n) {
+              const int cg = my_c0 + g * 16;
+              if (kSimple) {
+                if (cg + 16 > a.Tk) {   // the group that holds the end of the sequence (warp-uniform)
+  #pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (cg + i >= a.Tk) v[g * 16 + i] = 0xff800000u;
+                }
+              } else {
+                uint32_t bits = mid_range16(lo, hi, cg);
+                if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
+                if (bits != 0xffffu) {
+  #pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (!((bits >> i) & 1u)) v[g * 16 + i] = 0xff800000u;
+                }
               }
-            } else {
-              uint32_t bits = mid_range16(lo, hi, cg);
-              if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
+              m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 0]), __uint_as_float(v[g * 16 + 1]));
+              m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 2]), __uint_as_float(v[g * 16 + 3]));
+              m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 4]), __uint_as_float(v[g * 16 + 5]));
+              m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 6]), __uint_as_float(v[g * 16 + 7]));
+              m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 8]), __uint_as_float(v[g * 16 + 9]));
+              m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 10]), __uint_as_float(v[g * 16 + 11]));
+              m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 12]), __uint_as_float(v[g * 16 + 13]));
+              m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 14]), __uint_as_float(v[g * 16 + 15]));
+            }
+          }
+          m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+          // bounded logits: only the mask has to be applied (columns past the sequence end / the generic predicate)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 16 < my_n) {
+              const int cg = my_c0 + g * 16;
+              uint32_t bits = 0xffffu;
+              if (kSimple) {
+                if (cg + 16 > a.Tk) bits = cg >= a.Tk ? 0u : (0xffffu >> (cg + 16 - a.Tk));
+              } else {
+                bits = mid_range16(lo, hi, cg);
+                if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
+              }
               if (bits != 0xffffu) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                   if (!((bits >> i) & 1u)) v[g * 16 + i] = 0xff800000u;
               }
             }
-            m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 0]), __uint_as_float(v[g * 16 + 1]));
-            m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 2]), __uint_as_float(v[g * 16 + 3]));
-            m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 4]), __uint_as_float(v[g * 16 + 5]));
-            m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 6]), __uint_as_float(v[g * 16 + 7]));
-            m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 8]), __uint_as_float(v[g * 16 + 9]));
-            m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 10]), __uint_as_float(v[g * 16 + 11]));
-            m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 12]), __uint_as_float(v[g * 16 + 13]));
-            m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 14]), __uint_as_float(v[g * 16 + 15]));
           }
         }
-        m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
-      // ---- row maximum across the two halves (also orders B's P stores behind A's TMEM reads and vice versa)
-      if (r == 0 && half == 0) trace(0x290u + (f & 15u));
-      bars->row_max[slot][half][r] = m;
-      mid_named_barrier(1, 256);
-      if (r == 0 && half == 0) trace(0x220u + (f & 15u));
-      if (warp_live) {
+      float neg_m;
+      if (!P.bounded || !P.o_shared) {
+        // ---- row maximum across the two halves (with O inside the slot the barrier also orders B's P stores behind
+        //      A's TMEM reads)
+        if (r == 0 && half == 0) trace(0x290u + (f & 15u));
+        bars->row_max[slot][half][r] = m;
+        mid_named_barrier(1, 256);
+        if (r == 0 && half == 0) trace(0x220u + (f & 15u));
         m = fmaxf(m, bars->row_max[slot][half ^ 1][r]);
-        const float neg_m = (m == -INFINITY) ? 0.f : -m * a.scale_log2;
+      }
+      neg_m = P.bounded ? -P.bound_log2 : ((m == -INFINITY) ? 0.f : -m * a.scale_log2);
+      if (warp_live) {
         const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
         const float2 nm2 = make_float2(neg_m, neg_m);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-        const uint32_t tP = tS + (uint32_t)(my_c0 >> 1);
+        const uint32_t tP = tS + (half ? (uint32_t)P.pb_col : 0u);
         const uint32_t tSn = tmem + lane_base + (slot ^ 1u) * (uint32_t)P.slot_cols + (uint32_t)my_c0;
         // S(f+1) becomes ready somewhere inside this loop (it is issued behind P.V(f-1)): poll, and from then on refill
         // every consumed group of registers with the same columns of the next tile

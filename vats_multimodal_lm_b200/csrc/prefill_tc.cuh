@@ -69,6 +69,8 @@ struct TcParams {
   int order_softmax; // 1: the two softmax warpgroups take turns in the exponential phase (staggers the ping-pong)
   // fused output gather (vats_attn_prefill_gather): every staged O tile is stored into the gathered output of ALL
   // ranks (peer memory over NVLink) instead of the local output only
+  int bounded;       // 1: the caller guarantees |q.k| <= logit bound (qk-norm): no row maximum, no rescaling —
+  float bound_log2;  //    p = exp2(s * scale_log2 - bound_log2), bound_log2 = bound * scale * log2(e)
   int peers;         // 0 = plain launch (tmap_o); W = number of ranks whose gathered tensors receive the tiles
   int peer_first;    // first destination (each rank starts elsewhere, so no copy is hit by all ranks at once)
   int seq_off;       // this rank's first sequence / head inside the gathered [N_total, Tq, H_total, hd] tensor
@@ -614,16 +616,23 @@ prefill_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap tmap_q,
             if (!((kbits[c >> 5] >> (c & 31)) & 1u)) sr[c] = 0xff800000u;  // -inf
         }
 
-        // ---- row max of this tile (raw logits), in-thread
-        float mx[8];
+        // ---- row max of this tile (raw logits), in-thread.  With bounded logits (qk-norm: |q.k| <= bound) the bound
+        //      itself is the reference point: softmax is shift-invariant, so the 128 FMNMX per row and every rescale
+        //      of O disappear (m_used is set once and never moves).
+        float mt;
+        if (P.bounded) {
+          mt = P.bound_log2;
+        } else {
+          float mx[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(sr[i]);
+          for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(sr[i]);
 #pragma unroll
-        for (int c = 8; c < 128; c += 8)
+          for (int c = 8; c < 128; c += 8)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __uint_as_float(sr[c + i]));
-        const float mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) *
-                         a.scale_log2;  // scaled-log2 units (scale > 0)
+            for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __uint_as_float(sr[c + i]));
+          mt = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))) *
+               a.scale_log2;  // scaled-log2 units (scale > 0)
+        }
 
         // ---- lazy rescale of the running state
         float factor = 1.f;

@@ -187,7 +187,11 @@ struct PrefillArgs {
   // fused output gather (vats_attn_prefill_gather): `o` is unused, tiles go to o_ranks[0..world)
   void* const* o_ranks = nullptr;
   int world = 0, rank = 0, seq_off = 0, head_off = 0, N_total = 0, H_total = 0;
+  float logit_bound = 0.f;   // > 0: the caller guarantees |q.k| <= logit_bound for every (query, key) pair (qk-norm)
 };
+
+// bound on the scaled-log2 logits; 2 % head room for the bf16 rounding of unit-norm q / k
+float bound_log2_of(const PrefillArgs& A) { return A.logit_bound * 1.02f * A.scale * 1.4426950408889634f; }
 
 int validate_prefill(const PrefillArgs& A) {
   if (A.N < 0 || A.Tq < 0 || A.Tk < 0) return fail(VATS_ERR_INVALID_ARGUMENT, "negative size");
@@ -483,6 +487,8 @@ int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
   P.pairs = (P.a.hpg + 1) / 2;
   P.no_band = (!A.causal && A.left < 0 && A.right < 0) ? 1 : 0;
+  P.bounded = A.logit_bound > 0.f ? 1 : 0;
+  P.bound_log2 = bound_log2_of(A);
   // one staging mode per launch: if any of q / k / v cannot be addressed by TMA, all three use the LDG loaders
   const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
   if (any_ldg) {
@@ -672,6 +678,9 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;   // (3 is decided below, once o_bufs is known)
   P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
   P.cols_a = (P.n_pad + 31) / 32 * 16;
+  P.pb_col = P.o_shared ? P.cols_a : P.cols_a / 2;
+  P.bounded = A.logit_bound > 0.f ? 1 : 0;
+  P.bound_log2 = bound_log2_of(A);
   const long long q_bytes = 2LL * P.regions * vats::kMidQRegionBytes;
   const long long kv_stage = 2LL * P.regions * P.n_pad * 128;
   long long nkv = 0;
@@ -970,11 +979,14 @@ int vats_attn_prefill_ws(const void* q, const void* k, const void* v, void* o, c
                          const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
                          const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
                          const int64_t o_strides[3], float scale, int causal, int left, int right, int kernel,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         float logit_bound, void* workspace, size_t workspace_bytes, void* stream) {
   PrefillArgs A{q, k, v, o, q_valid, k_valid, N, Tq, Tk, H, G, hd, q_strides, k_strides, v_strides, o_strides,
                 scale, causal, left, right};
   A.ws = workspace;
   A.ws_bytes = workspace ? workspace_bytes : 0;
+  if (logit_bound < 0.f || !std::isfinite(logit_bound))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "logit_bound must be >= 0 and finite (0 = unknown)");
+  A.logit_bound = logit_bound;
   return prefill_impl(A, kernel, stream);
 }
 
@@ -983,8 +995,10 @@ int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* 
                              const uint8_t* k_valid, int N, int Tq, int Tk, int H, int G, int hd,
                              const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
                              const int64_t o_strides[3], float scale, int causal, int left, int right,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             float logit_bound, void* workspace, size_t workspace_bytes, void* stream) {
   g_launches = 0;
+  if (logit_bound < 0.f || !std::isfinite(logit_bound))
+    return fail(VATS_ERR_INVALID_ARGUMENT, "logit_bound must be >= 0 and finite (0 = unknown)");
   if (!o_ranks || world < 1 || world > vats::kTcMaxPeers || rank < 0 || rank >= world)
     return fail(VATS_ERR_INVALID_ARGUMENT, "fused gather: need 1 <= world <= %d output pointers and 0 <= rank < world",
                 vats::kTcMaxPeers);
@@ -1004,6 +1018,7 @@ int vats_attn_prefill_gather(const void* q, const void* k, const void* v, void* 
   A.head_off = head_offset;
   A.N_total = N_total;
   A.H_total = H_total;
+  A.logit_bound = logit_bound;
   int rc = validate_prefill(A);
   if (rc != VATS_OK) return rc;
   if ((rc = check_device()) != VATS_OK) return rc;

@@ -52,6 +52,11 @@ def setup_projections(d_model: int, num_heads: int, head_dim: int, use_fused_pro
     return q_proj, k_proj, v_proj, o_proj
 
 
+# |<q, k>| behind `apply_qk_norm` (unit vectors; RoPE is a rotation): what the modules promise the kernels as
+# `logit_bound` when use_qk_norm is set, so the row-maximum pass of the softmax is skipped
+QK_NORM_LOGIT_BOUND = 1.0
+
+
 def apply_qk_norm(query: torch.Tensor, key: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """L2-normalise q and k over head_dim (reference utils/attention_utils.py:99-102, eps = 1e-6)."""
     return F.normalize(query, p=2, dim=-1, eps=1e-6), F.normalize(key, p=2, dim=-1, eps=1e-6)
@@ -77,7 +82,7 @@ def _to_kernel_layout(x: torch.Tensor, pad: bool = True) -> torch.Tensor:
 
 def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float, causal: bool, left: int,
                    right: int, q_valid: Optional[torch.Tensor] = None, k_valid: Optional[torch.Tensor] = None,
-                   out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+                   out_dtype: Optional[torch.dtype] = None, logit_bound: float = 0.0) -> torch.Tensor:
     """q [N,Tq,H,hd], k/v [N,Tk,G,hd] (G heads, un-expanded) -> [N,Tq,H,hd].
 
     The one call that replaces `F.scaled_dot_product_attention` at the reference's three call sites.  Inputs are cast
@@ -88,5 +93,5 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: 
     # with bulk copies: no head-stride padding there
     pad = k.size(1) > 32
     o = ops.gqa_swa_prefill(_to_kernel_layout(q, pad), _to_kernel_layout(k, pad), _to_kernel_layout(v, pad), q_valid,
-                            k_valid, float(scale), bool(causal), int(left), int(right))
+                            k_valid, float(scale), bool(causal), int(left), int(right), 0, float(logit_bound))
     return o.to(out_dtype)

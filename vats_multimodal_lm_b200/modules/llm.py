@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
+from ._common import QK_NORM_LOGIT_BOUND, apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
 
 
 def _on_gpu(x: torch.Tensor) -> bool:
@@ -374,12 +374,14 @@ class Attention(nn.Module):
 
         cache_out = {"k": k.to(x.dtype), "v": v.to(x.dtype)} if use_cache else None
 
+        bound = QK_NORM_LOGIT_BOUND if use_qk_norm else 0.0   # unit-norm q, k (also the cached keys): |q.k| <= 1
+
         def core(q_, k_, v_):
             if fused:   # already bf16 in the kernels' layout: no second cast / pad pass
                 return ops.gqa_swa_prefill(q_, k_, v_, padding_mask, None, float(self.softmax_scale), bool(causal),
-                                           int(left), int(right)).to(x.dtype)
+                                           int(left), int(right), 0, bound).to(x.dtype)
             return attention_core(q_, k_, v_, scale=self.softmax_scale, causal=causal, left=left, right=right,
-                                  q_valid=padding_mask, out_dtype=x.dtype)
+                                  q_valid=padding_mask, out_dtype=x.dtype, logit_bound=bound)
 
         if cached:
             # intended contract of reference :508-516 — append at the layer's length, attend the cache

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
+from ._common import QK_NORM_LOGIT_BOUND, apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
 from .llm import RMSNorm, _on_gpu
 
 
@@ -132,6 +132,7 @@ class SpatialAttention(nn.Module):
         if not self.use_windowed_attn or mode == "reference_sdpa":
             left_window, right_window = -1, -1  # reference :601-603 (and its SDPA path never windows)
         scale = 1.0 / math.sqrt(self.head_dim)
+        bound = QK_NORM_LOGIT_BOUND if use_qk_norm else 0.0
         if _on_gpu(x) and x.dim() == 3 and x.size(1) > 0 and x.dtype in (torch.float32, torch.bfloat16) and not (
                 torch.is_grad_enabled() and (x.requires_grad or self.o_proj.weight.requires_grad)):
             # inference: qk-norm + 2-D RoPE + bf16 rounding + kernel layout in ONE launch straight from the projection's
@@ -145,10 +146,12 @@ class SpatialAttention(nn.Module):
             cos, sin, partner = self.rope.tables(T)
             q, k, v = ops.prefill_prepare_table_views(q.view(B, 1, T, H, hd), k.view(B, 1, T, G, hd), v.view(B, 1, T, G, hd),
                                                       cos, sin, partner, bool(use_qk_norm))
-            o = ops.gqa_swa_prefill(q, k, v, None, None, scale, False, int(left_window), int(right_window)).to(x.dtype)
+            o = ops.gqa_swa_prefill(q, k, v, None, None, scale, False, int(left_window), int(right_window), 0,
+                                    bound).to(x.dtype)
             return self.o_proj(o.reshape(B, T, self.d_model))
         q, k, v = self._setup_qkv(x, use_mqa=use_mqa, use_qk_norm=use_qk_norm)
-        o = attention_core(q, k, v, scale=scale, causal=False, left=left_window, right=right_window, out_dtype=x.dtype)
+        o = attention_core(q, k, v, scale=scale, causal=False, left=left_window, right=right_window, out_dtype=x.dtype,
+                           logit_bound=bound)
         return self.o_proj(o.reshape(x.size(0), x.size(1), self.d_model))
 
 

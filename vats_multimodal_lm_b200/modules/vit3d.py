@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._common import apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
+from ._common import QK_NORM_LOGIT_BOUND, apply_qk_norm, attention_core, get_default_window_mode, setup_projections, WINDOW_MODES
 from .llm import RMSNorm, _on_gpu
 
 
@@ -175,6 +175,7 @@ class SpatioTemporalAttention(nn.Module):
         left, right = window
         scale = 1.0 / math.sqrt(self.head_dim)
         H, G, hd = self.num_heads, self.query_groups, self.head_dim
+        bound = QK_NORM_LOGIT_BOUND if use_qk_norm else 0.0
         if _on_gpu(x) and x.dtype in (torch.float32, torch.bfloat16) and not (
                 torch.is_grad_enabled() and (x.requires_grad or self.w_o.weight.requires_grad)):
             # inference: qk-norm + 3-D RoPE + bf16 rounding + kernel layout in ONE launch, reading the projection in place
@@ -188,7 +189,7 @@ class SpatioTemporalAttention(nn.Module):
                 q5, k5, v5 = (t.permute(0, 2, 1, 3, 4) for t in (q5, k5, v5))
             cos, sin, partner = self.rope.tables(grid_shape, attn_mode)
             qk, kk, vk = ops.prefill_prepare_table_views(q5, k5, v5, cos, sin, partner, bool(use_qk_norm))
-            o = ops.gqa_swa_prefill(qk, kk, vk, None, k_valid, scale, False, int(left), int(right)).to(x.dtype)
+            o = ops.gqa_swa_prefill(qk, kk, vk, None, k_valid, scale, False, int(left), int(right), 0, bound).to(x.dtype)
             return o.reshape(qk.size(0), qk.size(1), self.d_model)
         q, k, v = self._setup_qkv(x, use_mqa, use_qk_norm, grid_shape, attn_mode)
         if attn_mode == "temporal":
@@ -198,10 +199,10 @@ class SpatioTemporalAttention(nn.Module):
                 buf.copy_(t5)
                 return buf.view(B * S, T, t5.size(3), self.head_dim)
             o = ops.gqa_swa_prefill(cast_transposed(q), cast_transposed(k), cast_transposed(v), None, k_valid, scale,
-                                    False, int(left), int(right)).to(x.dtype)
+                                    False, int(left), int(right), 0, bound).to(x.dtype)
             return o.reshape(B * S, T, self.d_model)
         o = attention_core(q, k, v, scale=scale, causal=False, left=left, right=right, k_valid=k_valid,
-                           out_dtype=x.dtype)
+                           out_dtype=x.dtype, logit_bound=bound)
         return o.reshape(q.size(0), q.size(1), self.d_model)
 
     def forward(self, x: torch.Tensor, grid_size: Tuple[int, int, int], use_mqa: bool, use_qk_norm: bool,

@@ -57,8 +57,11 @@ def _valid_u8(name: str, m: Optional[torch.Tensor], N: int, T: int, device) -> O
 @torch.library.custom_op("vats::gqa_swa_prefill", mutates_args=(), device_types="cuda")
 def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: Optional[torch.Tensor],
                     k_valid: Optional[torch.Tensor], scale: float, causal: bool, left: int, right: int,
-                    kernel: int = 0) -> torch.Tensor:
-    """q [N,Tq,H,hd], k/v [N,Tk,G,hd] (bf16, any strides with hd contiguous) -> o [N,Tq,H,hd] bf16."""
+                    kernel: int = 0, logit_bound: float = 0.0) -> torch.Tensor:
+    """q [N,Tq,H,hd], k/v [N,Tk,G,hd] (bf16, any strides with hd contiguous) -> o [N,Tq,H,hd] bf16.
+
+    logit_bound > 0 promises |<q, k>| <= logit_bound for every pair (1.0 behind the reference's qk-norm): the kernels
+    then skip the row-maximum pass (softmax is shift-invariant; same result).  0 = unknown."""
     _require_cuda_bf16("q", q)
     _require_cuda_bf16("k", k)
     _require_cuda_bf16("v", v)
@@ -132,7 +135,7 @@ def _(q, k, v, o, dout, q_valid, k_valid, scale, causal, left, right):
 
 
 def _prefill_setup_context(ctx, inputs, output):
-    q, k, v, q_valid, k_valid, scale, causal, left, right, _kernel = inputs
+    q, k, v, q_valid, k_valid, scale, causal, left, right, _kernel, _bound = inputs
     ctx.save_for_backward(q, k, v, output, q_valid, k_valid)
     ctx.attn_args = (scale, causal, left, right)
 
@@ -142,7 +145,7 @@ def _prefill_backward(ctx, dout):
     scale, causal, left, right = ctx.attn_args
     dq, dk, dv = torch.ops.vats.gqa_swa_prefill_bwd(q, k, v, o, dout.contiguous(), q_valid, k_valid, scale, causal, left,
                                                     right)
-    return dq, dk, dv, None, None, None, None, None, None, None
+    return dq, dk, dv, None, None, None, None, None, None, None, None
 
 
 gqa_swa_prefill.register_autograd(_prefill_backward, setup_context=_prefill_setup_context)
@@ -151,7 +154,7 @@ gqa_swa_prefill.register_autograd(_prefill_backward, setup_context=_prefill_setu
 def gqa_swa_prefill_gather(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
                            peer_ptrs: List[int], rank: int, seq_offset: int, head_offset: int,
                            q_valid: Optional[torch.Tensor], k_valid: Optional[torch.Tensor], scale: float, causal: bool,
-                           left: int, right: int) -> None:
+                           left: int, right: int, logit_bound: float = 0.0) -> None:
     """Local attention with the multi-GPU output gather fused into the kernel epilogue (vats_attn_prefill_gather).
 
     q [N,Tq,H,hd], k/v [N,Tk,G,hd] are this rank's units; `out` is this rank's copy of the gathered
@@ -189,7 +192,7 @@ def gqa_swa_prefill_gather(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, ou
                             N_total, H_total, qv.data_ptr() if qv is not None else None,
                             kv.data_ptr() if kv is not None else None, N, Tq, Tk, H, G, hd, qs, ks, vs,
                             out.stride()[:3], scale, causal, left, right, stream,
-                            ws.data_ptr() if ws is not None else None, ws_bytes)
+                            ws.data_ptr() if ws is not None else None, ws_bytes, logit_bound)
 
 
 def _tma_strides(*stride_sets) -> bool:
@@ -197,7 +200,7 @@ def _tma_strides(*stride_sets) -> bool:
 
 
 @gqa_swa_prefill.register_fake
-def _(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0):
+def _(q, k, v, q_valid, k_valid, scale, causal, left, right, kernel=0, logit_bound=0.0):
     return q.new_empty(q.shape, dtype=torch.bfloat16)
 
 

@@ -180,14 +180,15 @@ class FusedGather:
         self.shard = partition(B, G, self.world, self.rank)
 
     def run(self, ql: torch.Tensor, kl: torch.Tensor, vl: torch.Tensor, scale: float, causal: bool, left: int,
-            right: int, q_valid: Optional[torch.Tensor] = None, k_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+            right: int, q_valid: Optional[torch.Tensor] = None, k_valid: Optional[torch.Tensor] = None,
+            logit_bound: float = 0.0) -> torch.Tensor:
         """ql / kl / vl: this rank's units (`shard_qkv`).  Returns the gathered tensor (this rank's copy)."""
         from . import ops
         s = self.shard
         hpg = self.H // self.G
         self.handle.barrier()        # every rank is done with the previous contents
         ops.gqa_swa_prefill_gather(ql, kl, vl, self.local, self.peer_ptrs, self.rank, s.b0, s.g0 * hpg, q_valid, k_valid,
-                                   scale, causal, left, right)
+                                   scale, causal, left, right, logit_bound)
         self.handle.barrier()        # every rank's tiles have landed everywhere
         return self.local
 
