@@ -94,7 +94,8 @@ def gqa_swa_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_valid: 
         _ffi.prefill(q.data_ptr(), kp, vp, o.data_ptr(), qv.data_ptr() if qv is not None else None,
                      kv.data_ptr() if kv is not None else None,
                      N, Tq, Tk, H, G, hd, qs, ks, vs, o.stride()[:3],
-                     scale, causal, left, right, stream, kernel, ws.data_ptr() if ws is not None else None, ws_bytes)
+                     scale, causal, left, right, stream, kernel, ws.data_ptr() if ws is not None else None, ws_bytes,
+                     logit_bound)
     return o
 
 
