@@ -11,7 +11,8 @@ if "--pad" in sys.argv and hd % 8:
     def pad(x):
         buf = torch.zeros(*x.shape[:-1], (hd + 7) // 8 * 8, dtype=x.dtype, device="cuda"); buf[..., :hd] = x; return buf[..., :hd]
     q, k, v = pad(q), pad(k), pad(v)
-f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, False, -1, -1, ops.KERNEL_MID)
+bound = 1.0 if "--bound" in sys.argv else 0.0
+f = lambda: ops.gqa_swa_prefill(q, k, v, None, None, hd ** -0.5, False, -1, -1, ops.KERNEL_MID, bound)
 for _ in range(3): f()
 torch.cuda.synchronize()
 cap, NROLES = 4000, 4
