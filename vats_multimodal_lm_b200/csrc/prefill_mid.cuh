@@ -6,32 +6,35 @@
 // K / V of a (sequence, KV group) is ONE tile, so
 //   * K and V of the group are fetched once and stay in shared memory for ALL of the group's query heads and all of its
 //     query blocks (prefill_tc re-fetches them per head pair and per 128-token block);
-//   * S = Q.K^T is a single UMMA with N = keys rounded up to 16 (<= 256) and the softmax is single-pass and exact — no
+//   * S = Q.K^T is a single UMMA with N = keys rounded up to 16 (<= 256) and the softmax is exact over the whole row — no
 //     online rescaling, no running maximum, one S -> P round trip per tile;
 //   * the 128 rows of a tile are (token, head) pairs: the H/G query heads of the group are packed into the M dimension
 //     (TMA box {64, heads, 128/heads}), so 196 tokens x 4 heads are 7 tiles instead of 8 and the tile's rows are
 //     contiguous in q and o;
-//   * a tile's row is split between TWO threads (column halves, warpgroups A and B): each keeps its <= 128 logits in
-//     registers, so S is read from TMEM exactly once (TMEM reads run at 64 B/clk per SM sub-partition — a second
-//     pass over S costs as much as the exponentials); the halves exchange the row maximum through shared memory;
-//   * the write-out has its own warpgroup, so the exponentials of tile f+1 (the MUFU pipe is the co-critical
-//     resource here: 128 x 208 ex2 per tile) overlap P.V, the TMEM read of O and the TMA store of tile f;
-//   * two TMEM tile slots ping-pong, so the MMAs of one tile run under the softmax of the other.
-// (First version, measured on B200: one warpgroup per slot doing two TMEM passes and its own epilogue — every phase
-// ran latency-bound with one active warp per sub-partition: cfg3 0.218 ms, no better than the 128 x 128 tile kernel.)
+//   * the two softmax warpgroups each own ONE of the two TMEM tile slots (every second tile) and run half a tile apart:
+//     a thread streams its row through registers 32 columns at a time (double-buffered tcgen05.ld — a 128-column read
+//     costs ~50 clk, tools/micro/tmem_bw.cu), one pass for the row maximum and one for the exponentials (the first
+//     is skipped under a logit bound), and the dead time of one warpgroup (tile bookkeeping, barrier round trips,
+//     TMEM latency) hides behind the exponentials of the other — the MUFU pipe is the resource they share
+//     (128 x 208 ex2 per tile = 1664 clk per SM sub-partition);
+//   * the write-out has its own warpgroup, so P.V, the TMEM read of O and the TMA store of tile f overlap the
+//     softmax of tiles f+1, f+2;
+// History, measured on B200 (cfg3): (1) one warpgroup per slot doing softmax AND its own epilogue: 0.218 ms; (2) a row
+// split between two threads of two warpgroups working on the SAME tile, logits held in 128 registers, row maximum
+// exchanged through shared memory: 0.173 ms — both warpgroups stalled at the same points of every tile (and a
+// mbarrier.try_wait used as a poll suspended them for >1000 clk per tile: try_wait blocks, test_wait does not).
 //
 // Persistent CTAs (one per SM, 16 warps) walk the (sequence, KV group) items round-robin.
-//   warps 0-3 / 4-7   softmax warpgroups A / B: thread r of each owns tile row r (TMEM lane r), A the columns
-//                     [0, cols_a), B the columns [cols_a, n_pad)
+//   warps 0-3 / 4-7   softmax warpgroups: warpgroup h owns TMEM slot h (tiles f = h, h+2, ...), thread r tile row r
 //   warps 8-11        epilogue warpgroup: O from TMEM, 1/l, bf16, staging tile, TMA store (or coalesced stores)
 //   warps 12, 13, 14  TMA producers (one lane each): K ring, V ring, Q tiles
 //                     (kLdg instantiation: 96 loader threads stage K, Q, V with cp.async — rows TMA cannot address,
 //                     e.g. dense head_dim 66: 132-byte rows)
 //   warp 15           MMA issuer: S(f) = Q.K^T (SS), O(f) = P.V (TS, P from TMEM), in the order S(0) S(1) PV(0) S(2) PV(1) ...
-// TMEM: slot s holds S in n_pad columns; P (bf16) is written over S[0, n_pad/2) once both halves hold their logits
-// in registers.  When 2 * n_pad + hd_pad <= 512 (ViT shapes: 2 * 208 + 80) there is ONE O accumulator behind the two
-// slots: S(f+2) then only waits for P.V(f) to have consumed P(f) — in-order on the tensor pipe — and not for the
-// epilogue to drain O(f), which takes the TMEM read of O (64 B/clk) out of the S -> softmax -> P.V -> S loop.  Otherwise
+// TMEM: slot s holds S in n_pad columns; P (bf16) is written over S[0, n_pad/2) behind the reads.  When
+// 2 * n_pad + hd_pad <= 512 (ViT shapes: 2 * 208 + 80) there is ONE O accumulator behind the two slots: S(f+2) then
+// only waits for P.V(f) to have consumed P(f) — in-order on the tensor pipe — and not for the epilogue to drain O(f),
+// which takes the epilogue out of the S -> softmax -> P.V -> S loop.  Otherwise
 // (256 keys x hd 128) O accumulates inside the slot, in the consumed upper half of S, at o_off = ceil16(n_pad/2).
 #pragma once
 #include "mask.cuh"
@@ -50,13 +53,10 @@ struct MidParams {
   int hd_pad;          // head dim rounded up to 16 (MMA K of S, MMA N of P.V)
   int regions;         // ceil(hd_pad / 64) 128-byte swizzle regions per row
   int n_pad;           // keys rounded up to 16 (MMA N of S, K extent of P.V), <= 256
-  int cols_a;          // columns of a row owned by softmax warpgroup A (multiple of 16, <= 128); B owns the rest
   int slot_cols;       // TMEM columns between the two tile slots
   int o_shared;        // 1: ONE O accumulator behind both S slots (2 * n_pad + hd_pad <= 512): a slot is free for the
                        //    next S as soon as its P was consumed; 0: O lives inside each slot's consumed S columns
   int o_off;           // TMEM column of O: absolute (o_shared) or relative to the slot
-  int pb_col;          // TMEM column (relative to the slot) where warpgroup B writes its half of P: its OWN S columns
-                       // (cols_a) when O is shared — no ordering against A's reads needed — else right behind A's P
   int bounded;         // 1: the caller guarantees |q.k| <= logit bound (qk-norm): the row maximum is not computed,
                        //    p = exp2(s * scale_log2 - bound_log2) — softmax is shift-invariant, so the result is the same
   float bound_log2;    // logit bound * scale * log2(e)
@@ -103,8 +103,7 @@ struct MidTracer {
 struct MidBarriers {
   uint64_t q_full[2], q_empty[2], s_full[2], p_full[2], o_full[2], o_empty[2];
   uint64_t k_full[kMidMaxKv], k_empty[kMidMaxKv], v_full[kMidMaxKv], v_empty[kMidMaxKv];
-  float row_max[2][2][128];   // [slot][column half][row]: the halves' row maxima (raw logits)
-  float row_sum[2][2][128];   // [slot][column half][row]: the halves' row sums, read by the epilogue
+  float row_sum[2][128];      // [slot][row]: row sums of P, read by the epilogue
   uint32_t kbits[8][8];       // per softmax warp: k_valid of the current item as bit words (generic-mask path)
   uint32_t tmem_base;
   uint32_t pad;
@@ -249,7 +248,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
       mbar_init(smem_u32(&bars->q_full[s]), load_arrivals);
       mbar_init(smem_u32(&bars->q_empty[s]), 1);
       mbar_init(smem_u32(&bars->s_full[s]), 1);
-      mbar_init(smem_u32(&bars->p_full[s]), 256);
+      mbar_init(smem_u32(&bars->p_full[s]), 128);
       mbar_init(smem_u32(&bars->o_full[s]), 1);
       mbar_init(smem_u32(&bars->o_empty[s]), 128);
     }
@@ -319,7 +318,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
         // A tile's arrival is deferred until the next tile's copies are in flight — but never across a wait that may
         // depend on it (with a one-deep K ring the next item's k_empty needs S of the tile still pending here).
         auto wait_flush = [&](uint32_t bar, uint32_t parity, uint32_t tag) {
-          if (mbar_try_wait(bar, parity)) return;
+          if (mbar_test_wait(bar, parity)) return;
           if (pending != 0u) {
             cpasync_wait<0>();
             fence_proxy_async_smem();
@@ -425,10 +424,8 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
           const uint32_t tD = P.o_shared ? tmem_u + (uint32_t)P.o_off : tP + (uint32_t)P.o_off;
           const uint32_t v_lo = v_lo_base + (uint32_t)vs * kv_step;
           uint32_t acc = 0u;
-          const int ksteps_a = P.cols_a / 16;   // k-steps whose P comes from warpgroup A's columns
           for (int k = 0; k < ksteps_o; ++k) {
-            const uint32_t pcol = k < ksteps_a ? (uint32_t)k * 8u : (uint32_t)P.pb_col + (uint32_t)(k - ksteps_a) * 8u;
-            mma_ts_lohi(tD, tP + pcol, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc, leader);
+            mma_ts_lohi(tD, tP + (uint32_t)k * 8u, v_lo + (uint32_t)k * (2048u >> 4), hi_sw, idesc_o, acc, leader);
             acc = 1u;
           }
           tc_commit_pred(smem_u32(&bars->o_full[s]), leader);
@@ -474,7 +471,6 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
     }
   } else if (warp >= 8) {
     // ====================================================================== epilogue warpgroup (warps 8-11)
-    setmaxnreg_dec<96>();
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -496,7 +492,7 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
       mbar_wait_relaxed(smem_u32(&bars->o_full[slot]), u & 1u, 40);
       if (r == 0) trace(0x250u + (f & 15u));
       tc_fence_after();
-      const float l_sum = bars->row_sum[slot][0][r] + bars->row_sum[slot][1][r];
+      const float l_sum = bars->row_sum[slot][r];
       const float inv = (qok && l_sum > 0.f) ? 1.f / l_sum : 0.f;
       if (P.o_stage == 3) {
         // ---- dense row staging: lane's row at stage + lane * hd * 2 (exactly the box {pack*hd/2 words, 32/pack tokens}
@@ -639,198 +635,146 @@ prefill_mid_kernel(const MidParams P, const __grid_constant__ CUtensorMap tmap_q
     }
     if ((P.o_stage == 1 || P.o_stage == 3) && lane == 0) bulk_wait_group0();   // staged O tiles must be out before the CTA's smem goes away
   } else {
-    // ====================================================================== softmax warpgroups A (warps 0-3), B (4-7)
-    setmaxnreg_inc<176>();
-    const int half = warp >> 2;
+    // ====================================================================== softmax warpgroups (warps 0-3, 4-7)
+    // Warpgroup h owns TMEM slot h, i.e. every second tile of this CTA: the two run half a tile apart, so the
+    // per-tile bookkeeping, barrier round trips and TMEM latencies of one hide behind the exponentials of the other
+    // (the MUFU pipe is the resource they share).  Thread r owns tile row r (TMEM lane r) and streams it through
+    // registers 32 columns at a time, double-buffered: exact mode makes one pass for the row maximum and one for
+    // the exponentials (a TMEM read costs ~50 clk per 128 columns — tools/micro/tmem_bw.cu), bounded mode
+    // (qk-norm) the second pass only.  P (bf16) overwrites the slot's S columns in place, behind the reads.
+    setmaxnreg_inc<152>();
+    const int h = warp >> 2;
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    const int my_c0 = half ? P.cols_a : 0;                       // first column of this thread's share of the row
-    const int my_n = half ? P.n_pad - P.cols_a : P.cols_a;      // its width (multiple of 16, possibly 0 for B)
+    const uint32_t tS = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)h * (uint32_t)P.slot_cols;
     uint32_t* kb = bars->kbits[warp];
-    const bool use_kb = a.k_valid != nullptr;
+    const bool use_kb = !kSimple && a.k_valid != nullptr;
+    const int nch = (P.n_pad + 31) >> 5;
+    const bool tail16 = (P.n_pad & 16) != 0;   // the last chunk holds 16 columns (its upper half is never stored)
+    const uint32_t s_bar = smem_u32(&bars->s_full[h]);
+    const uint32_t p_bar = smem_u32(&bars->p_full[h]);
     MidTracer trace(P, 2);
-
-    // This thread's share of a row lives in v[] (one TMEM read per tile).  While the exponentials of tile f run, each
-    // group of 16 registers is refilled with the same columns of S(f+1) as soon as it has been consumed: the TMEM read
-    // (64 B/clk per SM — as long as the exponentials themselves) hides behind the MUFU work instead of preceding it.
-    uint32_t v[128];
-    bool prefetched = false;     // v[] already holds (or is receiving) this tile's logits
     MidCursor c{(int)blockIdx.x, 0};
-    MidTile t = mid_decode(P, c);
-    for (uint32_t f = 0; c.item < P.num_items; ++f) {
-      const uint32_t slot = f & 1u, u = f >> 1;
-      const uint32_t tS = tmem + lane_base + slot * (uint32_t)P.slot_cols;
+    mid_advance(P, c, h);
+    for (uint32_t j = 0; c.item < P.num_items; ++j, mid_advance(P, c, 2)) {
+      const MidTile t = mid_decode(P, c);
       const int tok = t.q0 + (r >> P.pack_shift);
-      const int tok_w = t.q0 + ((wq * 32) >> P.pack_shift);
-      const bool warp_live = tok_w < a.Tq;
-      const int tile_n = t.n;
-      // the next tile of this CTA (its slot is the other one); the prefetch needs the same warp to be live there
-      mid_advance(P, c, 1);
-      bool next_live = false;
-      if (c.item < P.num_items) {
-        t = mid_decode(P, c);
-        next_live = (t.q0 + ((wq * 32) >> P.pack_shift)) < a.Tq;
-      }
-
+      const bool warp_live = (t.q0 + ((wq * 32) >> P.pack_shift)) < a.Tq;
       int lo = 0, hi = a.Tk - 1;
       if (!kSimple && tok < a.Tq) {
-        const long long l = key_lo(a.mask, tok), h = key_hi(a.mask, tok);
+        const long long l = key_lo(a.mask, tok), hh = key_hi(a.mask, tok);
         lo = l < 0 ? 0 : (l > 256 ? 256 : (int)l);
-        hi = h < -1 ? -1 : (int)h;   // key_hi is already <= Tk - 1
+        hi = hh < -1 ? -1 : (int)hh;   // key_hi is already <= Tk - 1
       }
-      if (!kSimple && use_kb && warp_live) {
-        for (int w = 0; w < (P.n_pad + 31) / 32; ++w) {
+      if (use_kb && warp_live) {
+        for (int w = 0; w < nch; ++w) {
           const int key = w * 32 + lane;
-          const bool ok = key < a.Tk && a.k_valid[(long long)tile_n * a.Tk + key] != 0;
+          const bool ok = key < a.Tk && a.k_valid[(long long)t.n * a.Tk + key] != 0;
           const uint32_t bits = __ballot_sync(0xffffffffu, ok);
           if (lane == 0) kb[w] = bits;
         }
         __syncwarp();
       }
-
-      if (r == 0 && half == 0) trace(0x200u + (f & 15u));
-      if (!prefetched) {   // (a prefetching tile already waited for this S)
-        mbar_wait(smem_u32(&bars->s_full[slot]), u & 1u, 0x200u);
-        tc_fence_after();
-      }
-      if (r == 0 && half == 0) trace(0x210u + (f & 15u));
-
-      // ---- this thread's share of the row -> registers (one TMEM read), mask, local maximum
-      float m = -INFINITY;
-      if (warp_live) {
-        if (!prefetched) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g * 16 < my_n) tmem_ld_32x32b_x16(tS + (uint32_t)(my_c0 + g * 16), v + g * 16);
-        }
-        tmem_ld_wait();
-        if (r == 0 && half == 0) trace(0x280u + (f & 15u));
-        if (!P.bounded) {
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-  #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g * 16 < my_n) {
-              const int cg = my_c0 + g * 16;
-              if (kSimple) {
-                if (cg + 16 > a.Tk) {   // the group that holds the end of the sequence (warp-uniform)
-  #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (cg + i >= a.Tk) v[g * 16 + i] = 0xff800000u;
-                }
-              } else {
-                uint32_t bits = mid_range16(lo, hi, cg);
-                if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
-                if (bits != 0xffffu) {
-  #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (!((bits >> i) & 1u)) v[g * 16 + i] = 0xff800000u;
-                }
-              }
-              m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 0]), __uint_as_float(v[g * 16 + 1]));
-              m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 2]), __uint_as_float(v[g * 16 + 3]));
-              m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 4]), __uint_as_float(v[g * 16 + 5]));
-              m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 6]), __uint_as_float(v[g * 16 + 7]));
-              m0 = mid_max3(m0, __uint_as_float(v[g * 16 + 8]), __uint_as_float(v[g * 16 + 9]));
-              m1 = mid_max3(m1, __uint_as_float(v[g * 16 + 10]), __uint_as_float(v[g * 16 + 11]));
-              m2 = mid_max3(m2, __uint_as_float(v[g * 16 + 12]), __uint_as_float(v[g * 16 + 13]));
-              m3 = mid_max3(m3, __uint_as_float(v[g * 16 + 14]), __uint_as_float(v[g * 16 + 15]));
-            }
-          }
-          m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // allowed columns of chunk ci for this row, applied to the chunk in registers
+      auto mask_chunk = [&](uint32_t (&x)[32], int ci) {
+        uint32_t bits = 0xffffffffu;
+        if (kSimple) {
+          const int over = ci * 32 + 32 - a.Tk;   // columns of the chunk past the end of the sequence
+          if (over > 0) bits = over >= 32 ? 0u : (0xffffffffu >> over);
         } else {
-          // bounded logits: only the mask has to be applied (columns past the sequence end / the generic predicate)
+          bits = mid_range_word(lo, hi, ci * 32);
+          if (use_kb) bits &= kb[ci];
+        }
+        if (bits != 0xffffffffu) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g * 16 < my_n) {
-              const int cg = my_c0 + g * 16;
-              uint32_t bits = 0xffffu;
-              if (kSimple) {
-                if (cg + 16 > a.Tk) bits = cg >= a.Tk ? 0u : (0xffffu >> (cg + 16 - a.Tk));
-              } else {
-                bits = mid_range16(lo, hi, cg);
-                if (use_kb) bits &= kb[cg >> 5] >> (cg & 16);
-              }
-              if (bits != 0xffffu) {
+          for (int i = 0; i < 32; ++i)
+            if (!((bits >> i) & 1u)) x[i] = 0xff800000u;
+        }
+      };
+
+      if (r == 0 && h == 0) trace(0x200u + (j & 15u));
+      mbar_wait(s_bar, j & 1u, 0x200u);
+      tc_fence_after();
+      if (r == 0 && h == 0) trace(0x210u + (j & 15u));
+
+      float l_sum = 0.f;
+      if (warp_live) {
+        uint32_t xa[32], xb[32];
+        float neg_m = -P.bound_log2;
+        if (!P.bounded) {
+          // ---- pass 1: row maximum
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          auto max_chunk = [&](uint32_t (&x)[32], int ci) {
+            mask_chunk(x, ci);
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (!((bits >> i) & 1u)) v[g * 16 + i] = 0xff800000u;
-              }
+            for (int i = 0; i < 32; i += 8) {
+              m0 = mid_max3(m0, __uint_as_float(x[i + 0]), __uint_as_float(x[i + 1]));
+              m1 = mid_max3(m1, __uint_as_float(x[i + 2]), __uint_as_float(x[i + 3]));
+              m2 = mid_max3(m2, __uint_as_float(x[i + 4]), __uint_as_float(x[i + 5]));
+              m3 = mid_max3(m3, __uint_as_float(x[i + 6]), __uint_as_float(x[i + 7]));
+            }
+          };
+          tmem_ld_32x32b_x32(tS, xa);
+          tmem_ld_wait();
+#pragma unroll 1
+          for (int ci = 0; ci < nch; ci += 2) {
+            if (ci + 1 < nch) tmem_ld_32x32b_x32(tS + (uint32_t)(ci + 1) * 32u, xb);
+            max_chunk(xa, ci);
+            tmem_ld_wait();
+            if (ci + 1 < nch) {
+              if (ci + 2 < nch) tmem_ld_32x32b_x32(tS + (uint32_t)(ci + 2) * 32u, xa);
+              max_chunk(xb, ci + 1);
+              tmem_ld_wait();
             }
           }
+          const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          neg_m = (m == -INFINITY) ? 0.f : -m * a.scale_log2;
+          if (r == 0 && h == 0) trace(0x220u + (j & 15u));
         }
-      }
-      float neg_m;
-      if (!P.bounded || !P.o_shared) {
-        // ---- row maximum across the two halves (with O inside the slot the barrier also orders B's P stores behind
-        //      A's TMEM reads)
-        if (r == 0 && half == 0) trace(0x290u + (f & 15u));
-        bars->row_max[slot][half][r] = m;
-        mid_named_barrier(1, 256);
-        if (r == 0 && half == 0) trace(0x220u + (f & 15u));
-        m = fmaxf(m, bars->row_max[slot][half ^ 1][r]);
-      }
-      neg_m = P.bounded ? -P.bound_log2 : ((m == -INFINITY) ? 0.f : -m * a.scale_log2);
-      if (warp_live) {
+        // ---- pass 2: p = exp2(s * scale_log2 - m), row sum, P -> TMEM
         const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
         const float2 nm2 = make_float2(neg_m, neg_m);
         float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-        const uint32_t tP = tS + (half ? (uint32_t)P.pb_col : 0u);
-        const uint32_t tSn = tmem + lane_base + (slot ^ 1u) * (uint32_t)P.slot_cols + (uint32_t)my_c0;
-        // S(f+1) becomes ready somewhere inside this loop (it is issued behind P.V(f-1)): poll, and from then on refill
-        // every consumed group of registers with the same columns of the next tile
-        const uint32_t next_bar = smem_u32(&bars->s_full[slot ^ 1u]);
-        const uint32_t next_par = ((f + 1u) >> 1) & 1u;
-        bool ready = false;
-        int skipped = 0;    // groups [0, skipped) were consumed before S(f+1) was ready (steady state: none)
+        auto exp_chunk = [&](uint32_t (&x)[32], int ci) {
+          mask_chunk(x, ci);
+          uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g * 16 < my_n) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[g * 16 + i]), __uint_as_float(v[g * 16 + i + 1])), sc2, nm2);
-              const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[g * 16 + i + 2]), __uint_as_float(v[g * 16 + i + 3])), sc2, nm2);
-              const float2 p0 = make_float2(ex2(x0.x), ex2(x0.y));
-              const float2 p1 = make_float2(ex2(x1.x), ex2(x1.y));
-              sum_a = __fadd2_rn(sum_a, p0);
-              sum_b = __fadd2_rn(sum_b, p1);
-              pk[i >> 1] = pack_bf16x2(p0.x, p0.y);
-              pk[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-            }
-            tmem_st_32x32b_x8(tP + (uint32_t)(g * 8), pk);
-            if (next_live) {
-              if (!ready) {
-                ready = __all_sync(0xffffffffu, mbar_try_wait(next_bar, next_par));
-                if (ready) tc_fence_after();
-              }
-              if (ready)
-                tmem_ld_32x32b_x16(tSn + (uint32_t)(g * 16), v + g * 16);
-              else
-                skipped = g + 1;
-            }
-            if (r == 0 && half == 0 && (g == 0 || g == 3)) trace(0x2a0u + (uint32_t)g);
+          for (int i = 0; i < 32; i += 4) {
+            const float2 x0 = __ffma2_rn(make_float2(__uint_as_float(x[i]), __uint_as_float(x[i + 1])), sc2, nm2);
+            const float2 x1 = __ffma2_rn(make_float2(__uint_as_float(x[i + 2]), __uint_as_float(x[i + 3])), sc2, nm2);
+            const float2 p0 = make_float2(ex2(x0.x), ex2(x0.y));
+            const float2 p1 = make_float2(ex2(x1.x), ex2(x1.y));
+            sum_a = __fadd2_rn(sum_a, p0);
+            sum_b = __fadd2_rn(sum_b, p1);
+            pk[i >> 1] = pack_bf16x2(p0.x, p0.y);
+            pk[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+          }
+          tmem_st_32x32b_x8(tS + (uint32_t)ci * 16u, pk);
+          if (!(tail16 && ci == nch - 1)) tmem_st_32x32b_x8(tS + (uint32_t)ci * 16u + 8u, pk + 8);
+        };
+        tmem_ld_32x32b_x32(tS, xa);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int ci = 0; ci < nch; ci += 2) {
+          if (ci + 1 < nch) tmem_ld_32x32b_x32(tS + (uint32_t)(ci + 1) * 32u, xb);
+          exp_chunk(xa, ci);
+          tmem_ld_wait();
+          if (ci + 1 < nch) {
+            if (ci + 2 < nch) tmem_ld_32x32b_x32(tS + (uint32_t)(ci + 2) * 32u, xa);
+            exp_chunk(xb, ci + 1);
+            tmem_ld_wait();
           }
         }
-        if (next_live) {   // whatever was consumed before S(f+1) arrived
-          if (!ready) {
-            mbar_wait(next_bar, next_par, 0x201u);
-            tc_fence_after();
-          }
-#pragma unroll
-          for (int gg = 0; gg < 8; ++gg)
-            if (gg < skipped) tmem_ld_32x32b_x16(tSn + (uint32_t)(gg * 16), v + gg * 16);
-        }
-        bars->row_sum[slot][half][r] = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+        l_sum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
         tmem_st_wait();
-        prefetched = next_live;
-      } else {
-        bars->row_sum[slot][half][r] = 0.f;
-        prefetched = false;
       }
+      // the epilogue reads row_sum of the slot's previous tile before it releases o_empty: do not overwrite it earlier
+      // (short rows: this softmax can finish before the epilogue got to tile f-2)
+      if (j > 0) mbar_wait(smem_u32(&bars->o_empty[h]), (j - 1u) & 1u, 0x202u);
+      bars->row_sum[h][r] = l_sum;
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[slot]));
-      if (r == 0 && half == 0) trace(0x230u + (f & 15u));
+      mbar_arrive(p_bar);
+      if (r == 0 && h == 0) trace(0x230u + (j & 15u));
     }
   }
 

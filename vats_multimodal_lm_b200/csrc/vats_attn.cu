@@ -677,8 +677,6 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   }
   P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;   // (3 is decided below, once o_bufs is known)
   P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
-  P.cols_a = (P.n_pad + 31) / 32 * 16;
-  P.pb_col = P.o_shared ? P.cols_a : P.cols_a / 2;
   P.bounded = A.logit_bound > 0.f ? 1 : 0;
   P.bound_log2 = bound_log2_of(A);
   const long long q_bytes = 2LL * P.regions * vats::kMidQRegionBytes;
