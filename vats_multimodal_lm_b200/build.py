@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared", "--use_fast_math", "-Xptxas", "-v", *([f"-DVATS_MBAR_TIMEOUT_CYCLES={os.environ['VATS_MBAR_TIMEOUT_CYCLES']}"] if os.environ.get("VATS_MBAR_TIMEOUT_CYCLES") else []),
     *(["-DVATS_ENABLE_TRACE"] if os.environ.get("VATS_ENABLE_TRACE") else []),
     *(["-DVATS_MBAR_DEBUG"] if os.environ.get("VATS_MBAR_DEBUG") else []),
+    *(os.environ["VATS_EXTRA_NVCC_FLAGS"].split() if os.environ.get("VATS_EXTRA_NVCC_FLAGS") else []),   # A/B builds
 ]
 
 
