@@ -504,6 +504,30 @@ def bench_prefill_cfg(c, peaks, steps, warmup, world, rank, shard: bool, layout:
         res["error_vs_oracle"] = sampled_error(c, q, k, v, o)
     except Exception as e:
         res["error_vs_oracle"] = {"error": f"{type(e).__name__}: {e}"}
+    # The same workload the way the drop-in modules call it behind qk-norm (unit-norm q, k: logit_bound = 1.0, the
+    # kernels skip the row maximum).  Reported beside the exact-maximum time above, never instead of it.
+    bstep = lambda: ops.gqa_swa_prefill(q, k, v, None, None, scale, c["causal"], c["left"], right, 0, 1.0)
+    for _ in range(warmup):
+        ob = bstep()
+    bevs = []
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ob = bstep()
+        b.record()
+        bevs.append((a, b))
+    torch.cuda.synchronize()
+    bper = [a.elapsed_time(b) for a, b in bevs]
+    res["qk_norm_logit_bound"] = dict(ms_compute=max_over_ranks(statistics.mean(bper), world), ms_min=min(bper),
+                                      logit_bound=1.0, max_abs_vs_exact_path=(ob.float() - o.float()).abs().max().item(),
+                                      note="modules/_common.py QK_NORM_LOGIT_BOUND: q, k are l2-normalised by qk-norm")
+    try:
+        res["qk_norm_logit_bound"]["error_vs_oracle"] = sampled_error(c, q, k, v, ob)
+    except Exception as e:
+        res["qk_norm_logit_bound"]["error_vs_oracle"] = {"error": f"{type(e).__name__}: {e}"}
+    del ob
 
     if e2e and world == 1:
         # end to end through the public op with HOST buffers: pinned q/k/v -> H2D, kernel, D2H of o, every step
