@@ -33,9 +33,15 @@ W = {
 def main():
     name = sys.argv[1]
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    if name == "cfg2":
-        B, S, H, G, hd, left = 64, 8192, 32, 8, 128, 4096
+    if name in ("cfg2", "cfg2m"):
+        B, S, H, G, hd, left = (64, 8192, 32, 8, 128, 4096) if name == "cfg2" else (64, 8192, 24, 8, 60, 4096)
         kc, vc, q = rnd((B, S, G, hd), 1, True), rnd((B, S, G, hd), 2, False), rnd((B, H, hd), 3, True)
+        if hd % 8:   # the KVCache module keeps rows of hd rounded up to 8 elements (TMA-addressable)
+            def pad(x):
+                buf = torch.zeros(*x.shape[:-1], (hd + 7) // 8 * 8, dtype=x.dtype, device="cuda")
+                buf[..., :hd] = x
+                return buf[..., :hd]
+            kc, vc = pad(kc), pad(vc)
         lens = torch.full((B,), S, dtype=torch.int32, device="cuda")
         for _ in range(reps):
             o = ops.gqa_swa_decode(q, kc, vc, lens, hd ** -0.5, left)
