@@ -173,3 +173,51 @@ def test_bounded_logits_skip_the_row_maximum_and_give_the_same_softmax(shape, ke
         ref = oracle_prefill(q, k, v, scale, causal, left, right, None, kvm)
         check_close(o_b, ref, f"bounded {shape} causal={causal} ({left},{right}) kv={use_kv}")
         assert (o_b.float() - o_e.float()).abs().max().item() <= 2e-2   # both within the tolerance of the same oracle
+
+
+# (N, Tq, Tk, H, G, hd): sequences whose last tile holds only a few (token, head) rows
+RESIDUAL_SHAPES = [
+    (5, 196, 196, 4, 2, 72),      # cfg3 geometry: 2 heads packed, 3 full tiles + 4 tokens x 2 heads
+    (3, 196, 196, 8, 2, 66),      # cfg4a geometry, DENSE hd 66: repack + TMA, 6 full tiles + 4 tokens x 4 heads
+    (3, 196, 196, 8, 2, 72),      # the same with TMA-addressable rows
+    (7, 33, 33, 8, 1, 64),        # 8 heads packed: 2 full tiles + 1 token; n_pad 48 (odd 16-key block)
+    (4, 130, 130, 2, 2, 48),      # no packing: one full tile + 2 tokens, hd 48 in a 64-wide tile
+    (4, 140, 200, 4, 4, 60),      # Tq != Tk, dense hd 60 (repack), 12 residual rows
+    (2, 72, 256, 4, 2, 80),       # 256 keys, hd 80, 64-token tiles: 1 full tile + 8 tokens x 2 heads
+    (300, 68, 100, 4, 2, 64),     # many items per CTA
+]
+
+
+@pytest.mark.parametrize("bound", [0.0, 1.0], ids=["exact", "bounded"])
+@pytest.mark.parametrize("shape", RESIDUAL_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_mid_residual_query_tokens(shape, bound):
+    """Unmasked geometries whose last tile is almost empty, exact and bounded-logit softmax: every row — the residual
+    ones included — against the oracle and against the tile kernel."""
+    N, Tq, Tk, H, G, hd = shape
+    q, k, v = make_qkv(N, Tq, Tk, H, G, hd, seed=sum(shape))
+    scale = 1.0 / math.sqrt(hd)
+    o = run_prefill(q, k, v, scale, False, -1, -1, kernel=MID, logit_bound=bound)
+    assert _ffi.last_kernel() == "prefill_mid"
+    ref = oracle_prefill(q, k, v, scale, False, -1, -1)
+    check_close(o, ref, f"{shape} bound={bound}")
+    check_close(o[:, -4:], ref[:, -4:], f"{shape} last tokens")
+    o_tc = run_prefill(q, k, v, scale, False, -1, -1, kernel=ops.KERNEL_TCGEN05)
+    assert (o.float() - o_tc.float()).abs().max().item() <= 2e-2
+
+
+def test_repack_chunk_kernel_strided_sources():
+    """The repack route (rows TMA cannot address) with dense and strided hd-66 / hd-60 sources: views of a fused QKV
+    projection, token-strided views, 4-byte aligned bases."""
+    N, T, H, G, hd = 3, 150, 8, 2, 66
+    g = torch.Generator().manual_seed(77)
+    fused = torch.nn.functional.normalize(torch.randn(N, T, (H + 2 * G) * hd + 2, generator=g), dim=-1).bfloat16().cuda()
+    body = fused[..., 2:]   # 4-byte aligned base
+    q = body[..., : H * hd].unflatten(-1, (H, hd))
+    k = body[..., H * hd: (H + G) * hd].unflatten(-1, (G, hd))
+    v = body[..., (H + G) * hd:].unflatten(-1, (G, hd))
+    scale = hd ** -0.5
+    for kernel in (MID, ops.KERNEL_TCGEN05):
+        o = ops.gqa_swa_prefill(q, k, v, None, None, scale, False, -1, -1, kernel)
+        torch.cuda.synchronize()
+        assert _ffi.last_launch_count() == 2   # repack + the TMA-fed kernel
+        check_close(o, oracle_prefill(q.cpu(), k.cpu(), v.cpu(), scale, False, -1, -1), f"fused view kernel={kernel}")

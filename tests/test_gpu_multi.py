@@ -84,3 +84,38 @@ def test_sharded_gathers_match_single_gpu_world2():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world)), dict(results)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_two_devices():
+    """One thread launching on cuda:0 and then on cuda:1: the opt-in shared-memory attribute of every large-smem kernel
+    (tile, resident-K/V, short-sequence, decode) is per device — a cache that is not keyed on the device makes the
+    second device's launches fail with 'invalid argument'."""
+    import math
+
+    from conftest import make_qkv
+    from gpu_util import check_close, oracle_prefill, run_prefill
+    from oracle import decode_explicit
+    from vats_multimodal_lm_b200 import ops
+
+    cases = [((2, 300, 300, 4, 2, 64), True, 100, 0),       # tile kernel
+             ((80, 196, 196, 4, 2, 72), False, -1, -1),     # resident-K/V kernel
+             ((40, 8, 8, 8, 2, 66), False, -1, -1)]         # short-sequence kernel
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        for shape, causal, left, right in cases:
+            N, Tq, Tk, H, G, hd = shape
+            q, k, v = make_qkv(N, Tq, Tk, H, G, hd, seed=N)
+            scale = 1.0 / math.sqrt(hd)
+            o = run_prefill(q, k, v, scale, causal, left, right, device=dev)
+            torch.cuda.synchronize(dev)
+            assert o.device == torch.device(dev)
+            check_close(o, oracle_prefill(q, k, v, scale, causal, left, right), f"{dev} {shape}")
+        B, S, H, G, hd = 3, 700, 8, 2, 128
+        g = torch.Generator().manual_seed(5)
+        kc = torch.nn.functional.normalize(torch.randn(B, S, G, hd, generator=g), dim=-1).bfloat16()
+        vc = torch.randn(B, S, G, hd, generator=g).bfloat16()
+        qd = torch.nn.functional.normalize(torch.randn(B, H, hd, generator=g), dim=-1).bfloat16()
+        lens = torch.tensor([700, 1, 333], dtype=torch.int32)
+        o = ops.gqa_swa_decode(qd.to(dev), kc.to(dev), vc.to(dev), lens.to(dev), hd ** -0.5, 256)
+        torch.cuda.synchronize(dev)
+        check_close(o, decode_explicit(qd, kc, vc, lens, hd ** -0.5, 256), f"{dev} decode")

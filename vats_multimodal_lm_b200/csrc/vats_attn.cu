@@ -462,11 +462,32 @@ int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st, 
     if (i == 1) { B.k = t.dst; B.ks = new_str[1]; }
     if (i == 2) { B.v = t.dst; B.vs = new_str[2]; }
   }
-  long long blocks = (max_rows + vats::kRepackWarps * vats::kRepackRows - 1) / (vats::kRepackWarps * vats::kRepackRows);
-  const long long cap = (long long)sm_count() * 64;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  vats::repack_kernel<<<dim3((unsigned)blocks, (unsigned)nrep), vats::kRepackWarps * 32, 0, st>>>(R);
+  static int chunk_env = -1;
+  if (chunk_env < 0) {
+    const char* e = getenv("VATS_REPACK_CHUNK");  // tuning knob: 0 = the row-per-warp copy kernel
+    chunk_env = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const long long cpr = hd_pad / 8;
+  if (chunk_env && max_rows * cpr < 0x7fffffffLL) {
+    // one thread per 16-byte destination chunk (repack.cuh)
+    vats::tc_find_divisor((unsigned)cpr, R.div_cpr);
+    for (int i = 0; i < nrep; ++i) {
+      vats::tc_find_divisor((unsigned)R.t[i].heads, R.t[i].div_heads);
+      vats::tc_find_divisor((unsigned)R.t[i].T, R.t[i].div_T);
+    }
+    const long long per_block = (long long)vats::kRepackChunkThreads * vats::kRepackChunkUnroll;
+    long long blocks = (max_rows * cpr + per_block - 1) / per_block;
+    const long long cap = (long long)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    vats::repack_chunk_kernel<<<dim3((unsigned)blocks, (unsigned)nrep), vats::kRepackChunkThreads, 0, st>>>(R);
+  } else {
+    long long blocks = (max_rows + vats::kRepackWarps * vats::kRepackRows - 1) / (vats::kRepackWarps * vats::kRepackRows);
+    const long long cap = (long long)sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    vats::repack_kernel<<<dim3((unsigned)blocks, (unsigned)nrep), vats::kRepackWarps * 32, 0, st>>>(R);
+  }
   int rc = VATS_OK;
   if (cudaGetLastError() != cudaSuccess) {
     rc = fail(VATS_ERR_CUDA, "repack kernel launch failed");
@@ -657,11 +678,12 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.tok_per_tile = 128 >> P.pack_shift;
   P.q_tiles = (A.Tq + P.tok_per_tile - 1) / P.tok_per_tile;
   P.head_sets = hpg / pack;
+  const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
+  P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
   const long long tpi = (long long)P.q_tiles * P.head_sets;
   if (tpi > 0x3fffffLL) return -1;
   P.tiles_per_item = (int)tpi;
   P.num_items = A.N * A.G;
-  const bool any_ldg = pl.q == LoadMode::kLdg || pl.k == LoadMode::kLdg || pl.v == LoadMode::kLdg;
   if (any_ldg) {
     // rows TMA cannot address (dense hd 66 / 60): with caller-owned scratch, one streaming repack + the TMA-fed
     // kernel (cfg4a dense: 0.25 + 0.53 ms) beats the in-kernel cp.async staging (2.0 ms: 96 loader threads issuing
@@ -676,7 +698,6 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
     P.ldg_vec = (A.hd % 4 == 0 && al8(A.q, A.qs) && al8(A.k, A.ks) && al8(A.v, A.vs)) ? 2 : 1;
   }
   P.o_stage = plan_load(A.o, A.hd, A.os) == LoadMode::kTma ? 1 : 2;   // (3 is decided below, once o_bufs is known)
-  P.simple_mask = (!A.causal && A.left < 0 && A.right < 0 && !A.q_valid && !A.k_valid) ? 1 : 0;
   P.bounded = A.logit_bound > 0.f ? 1 : 0;
   P.bound_log2 = bound_log2_of(A);
   const long long q_bytes = 2LL * P.regions * vats::kMidQRegionBytes;
@@ -912,7 +933,10 @@ int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUt
   // the latency-bandwidth product needs only add DRAM page conflicts.
   int max_stages = 48;
   while (vats::decode_mma_smem_bytes<HD, NCW, SK>(max_stages) > 227 * 1024 && max_stages > 2) --max_stages;
-  int stages = 2 * NCW < max_stages ? 2 * NCW : max_stages;
+  // Tiles of <= 64 columns (hd 60 / 64: 8 KB stages) take three stages per consumer warp: cfg2-medium 8 stages 0.135,
+  // 12 stages 0.129, 16 stages 0.138, 24 stages 0.143 ms (tools/run_workload.py cfg2m --time, launch latency included).
+  const int want_stages = (HD <= 64 ? 3 : 2) * NCW;
+  int stages = want_stages < max_stages ? want_stages : max_stages;
   if (const char* e = getenv("VATS_DECODE_STAGES")) {  // tuning / debugging knob
     const int want = atoi(e);
     if (want >= 2 && want <= max_stages) stages = want;
