@@ -697,6 +697,66 @@ def bench_decode_secondary(c, peaks, steps, world, rank):
                 l2="inputs larger than L2")
 
 
+TRAIN_CFG = dict(name="cfg1_llm_train_step_T2048", N=8, T=2048, H=24, G=8, hd=60, causal=True, left=384)
+
+
+def bench_backward(c, peaks, steps, rank):
+    """Forward + backward of the core through autograd (reference training loop
+    training/transformers/nlp/loops/training_loop.py:54-65): vats::gqa_swa_prefill with requires_grad inputs in the
+    modules' layout, dO ~ N(0,1).  Forward and backward timed separately with CUDA events; gradients of a few sampled
+    rows are checked against torch.autograd on the fp32 oracle."""
+    from vats_multimodal_lm_b200 import _ffi, ops
+    from oracle import mask_predicate, sdpa_explicit
+    dev = torch.device("cuda", torch.cuda.current_device())
+    N, T, H, G, hd = c["N"], c["T"], c["H"], c["G"], c["hd"]
+    q, k, v = _gen_prefill_inputs(c, N, G, rank, dev, "module")
+    q, k, v = q.detach().requires_grad_(True), k.detach().requires_grad_(True), v.detach().requires_grad_(True)
+    do = gen_unit_bf16((N, T, H, hd), 9234 + rank, dev, False)
+    scale = hd ** -0.5
+    fwd = lambda: ops.gqa_swa_prefill(q, k, v, None, None, scale, c["causal"], c["left"], 0, 0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        o = fwd()
+        o.backward(do)
+        q.grad = k.grad = v.grad = None
+    tf, tb = [], []
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    for _ in range(steps):
+        flush.zero_()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        o = fwd()
+        e[1].record()
+        o.backward(do)
+        e[2].record()
+        torch.cuda.synchronize()
+        tf.append(e[0].elapsed_time(e[1]))
+        tb.append(e[1].elapsed_time(e[2]))
+        if _ < steps - 1:
+            q.grad = k.grad = v.grad = None
+    kernel = _ffi.last_kernel()
+    clocks = sampler.stop()
+    # gradient parity on one sequence, fp32 oracle + torch.autograd
+    qc, kc, vc = (t[:1].detach().float().cpu().requires_grad_(True) for t in (q, k, v))
+    ref = sdpa_explicit(qc, kc, vc, mask_predicate(1, T, T, c["causal"], c["left"], 0), scale)
+    ref.backward(do[:1].float().cpu())
+    errs = {}
+    for name, g, r in (("dq", q.grad, qc.grad), ("dk", k.grad, kc.grad), ("dv", v.grad, vc.grad)):
+        d = g[:1].float().cpu() - r
+        errs[name] = dict(max_abs=d.abs().max().item(), rel_l2=(d.norm() / r.norm()).item())
+    ms_f, ms_b = statistics.mean(tf), statistics.mean(tb)
+    fl = prefill_flops(c)
+    return dict(ms_forward=ms_f, ms_backward=ms_b, iterations=steps, kernel_last=kernel, clocks=clocks,
+                tflops_forward=fl / (ms_f * 1e-3) / 1e12, tflops_backward=2.5 * fl / (ms_b * 1e-3) / 1e12,
+                flops_forward=fl, flops_backward=2.5 * fl, tokens_per_s=N * T / ((ms_f + ms_b) * 1e-3),
+                grad_error_vs_autograd_of_oracle=errs, sequences_checked=1,
+                l2="flushed between iterations", layout="module layout (head stride padded to 8 elements)",
+                note="backward = recompute of the row statistics + dQ kernel + dK/dV kernel (mma.sync, deterministic); "
+                     "2.5x the forward's algorithmic FLOPs (5 matmuls vs 2), allowed pairs only; timings include the "
+                     "autograd dispatch")
+
+
 def cpu_baseline_decode():
     """Oracle-side port of the reference CPU path on a bounded sample, rank 0 / N=1 only."""
     from oracle.cpu_baseline import reference_decode_cpu, time_callable
@@ -747,6 +807,11 @@ def run_ours(args):
             other[CFG2_MEDIUM["name"]] = bench_decode_secondary(CFG2_MEDIUM, peaks, max(20, min(args.steps, 100)), world, rank)
         except Exception as e:
             other[CFG2_MEDIUM["name"]] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            try:
+                other[TRAIN_CFG["name"]] = bench_backward(TRAIN_CFG, peaks, 20, rank)
+            except Exception as e:
+                other[TRAIN_CFG["name"]] = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if rank == 0 and world == 1:
         try:

@@ -5,6 +5,9 @@ print(f"decode: value={d['value']:.0f} GB/s achieved={r['achieved']:.0f} ({100*r
 for k, v in d.get("other_workloads", {}).items():
     if "error" in v:
         print(k, "ERROR", v["error"]); continue
+    if "ms_forward" in v:
+        print(f"{k:26s} fwd {v['ms_forward']:.4f} ms ({v['tflops_forward']:.1f} TFLOP/s)  bwd {v['ms_backward']:.4f} ms ({v['tflops_backward']:.1f} TFLOP/s)")
+        continue
     rf = v["roofline"]
     extra = f" +allgather {v['ms_compute_plus_allgather']:.3f} ms" if "ms_compute_plus_allgather" in v else ""
     if "ms_compute_plus_allgather_overlapped" in v:
@@ -13,6 +16,6 @@ for k, v in d.get("other_workloads", {}).items():
         extra += f" (peer writes {v['ms_compute_plus_peer_gather_overlapped']:.3f} ms)"
     if "peer_gather_error" in v:
         extra += " peer_gather_error=" + v["peer_gather_error"][:80]
-    print(f"{k:26s} {v['ms_compute']:.4f} ms  {v['tflops']:8.1f} TFLOP/s {v['gbs']:8.1f} GB/s  {rf['bound']} frac={100*rf['frac']:.1f}%{extra}")
+    print(f"{k:26s} {v['ms_compute']:.4f} ms  {v.get('tflops', 0.0):8.1f} TFLOP/s {v['gbs']:8.1f} GB/s  {rf['bound']} frac={100*rf['frac']:.1f}%{extra}")
 if d.get("cpu_baseline"): print("cpu_baseline", d["cpu_baseline"])
 print("clocks", d.get("clocks"))
