@@ -271,9 +271,10 @@ def bench_decode(args, world, peaks):
 
     # ---- end to end through the public ops with HOST buffers: H2D of the step's projected q and new k/v (pinned),
     #      fused qk-norm + RoPE + cache append (vats::decode_prepare), decode, D2H of the result, every step
-    qh = q.cpu().pin_memory()
-    knh = kc[:, S - 1].cpu().pin_memory()
-    vnh = vc[:, S - 1].cpu().pin_memory()
+    # (the new token's q, k, v arrive as ONE host buffer [B, H + 2G, hd] — the layout of the reference's fused w_qkv
+    #  projection, src/optimized_attention.py:437-461 — so a step is two H2D copies: that buffer and the lengths)
+    G = c["G"]
+    qkv_h = torch.cat([q.cpu(), kc[:, S - 1].cpu(), vc[:, S - 1].cpu()], dim=1).pin_memory()
     lens_h = lens.cpu().pin_memory()
     oh = torch.empty((B, H, hd), dtype=torch.bfloat16).pin_memory()
 
@@ -282,9 +283,8 @@ def bench_decode(args, world, peaks):
     cos_t, sin_t = torch.cos(torch.outer(pos, inv_freq)), torch.sin(torch.outer(pos, inv_freq))
 
     def e2e_step():
-        qd = qh.to(dev, non_blocking=True)
-        kn = knh.to(dev, non_blocking=True)
-        vn = vnh.to(dev, non_blocking=True)
+        qkv = qkv_h.to(dev, non_blocking=True)
+        qd, kn, vn = qkv[:, :H], qkv[:, H:H + G], qkv[:, H + G:]
         ld = lens_h.to(dev, non_blocking=True)
         # L2-normalise + rotate q and k at position seq_len-1, append k/v there (one launch), then attend
         qr = ops.decode_prepare(qd, kn, vn, kc, vc, ld, cos_t, sin_t, True, 1e-6)
@@ -312,9 +312,8 @@ def bench_decode(args, world, peaks):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             def body():
-                qd = qh.to(dev, non_blocking=True)
-                kn = knh.to(dev, non_blocking=True)
-                vn = vnh.to(dev, non_blocking=True)
+                qkv = qkv_h.to(dev, non_blocking=True)
+                qd, kn, vn = qkv[:, :H], qkv[:, H:H + G], qkv[:, H + G:]
                 ld = lens_h.to(dev, non_blocking=True)
                 qr = ops.decode_prepare(qd, kn, vn, kc, vc, ld, cos_t, sin_t, True, 1e-6)
                 o = ops.gqa_swa_decode(qr, kc, vc, ld, scale, left)
@@ -348,7 +347,7 @@ def bench_decode(args, world, peaks):
         e2e_graph = world * nbytes / (max_over_ranks(t1 - t0, world) / args.steps) / 1e9
     clocks = sampler.stop()   # sampled over the device-timed region and the end-to-end region (both under load)
     e2e_value = e2e_graph if e2e_graph is not None else e2e_eager
-    h2d = qh.numel() * 2 + knh.numel() * 2 + vnh.numel() * 2 + lens_h.numel() * 4
+    h2d = qkv_h.numel() * 2 + lens_h.numel() * 4
     d2h = oh.numel() * 2
 
     # DRAM traffic of the dominant kernel cannot be measured without a profiler: it comes from the committed ncu
