@@ -23,10 +23,15 @@
 #include "decode_mma.cuh"   // ldmatrix / mma.sync wrappers
 #include "mask.cuh"
 #include "prefill_simt.cuh" // PrefillParams
+#include "prefill_tc.cuh"   // cp.async helpers
 
 namespace vats {
 
+#ifndef VATS_BWD_OCC   // A/B knob: 1 = ask ptxas for 3 CTAs per SM up to head dim 64 (2 up to 96)
+#define VATS_BWD_OCC 1
+#endif
 constexpr int kBwdThreads = 128;
+constexpr int bwd_min_blocks(int ks) { return VATS_BWD_OCC ? (ks <= 4 ? 3 : (ks <= 6 ? 2 : 1)) : 1; }
 constexpr int kBwdBM = 64;   // query rows per block
 constexpr int kBwdBN = 64;   // keys per block
 
@@ -41,21 +46,49 @@ struct BwdParams {
   float* dsum;                   // [N, H, Tq] D_i
   float scale;
   int hd_pad;                    // head dim rounded up to 16
+  int vec16;                     // 1: q, k, v, o, dout have 16-byte aligned bases and strides: tiles are staged with
+                                 // 16-byte cp.async copies (else 4-byte)
 };
 
+// dQ kernel: 4 tiles (Q / dO / O, then two K / V pairs); dK/dV kernel: 6 tiles (K, V, two Q / dO pairs) + two lse / D pairs
 __host__ __device__ inline size_t bwd_smem_bytes(int hd_pad) {
-  return (size_t)4 * kBwdBM * (hd_pad + 8) * 2 + 2 * kBwdBM * sizeof(float);
+  return (size_t)6 * kBwdBM * (hd_pad + 8) * 2 + 4 * kBwdBM * sizeof(float);
 }
 
-// rows [row0, row0 + 64) x hd of a row-strided bf16 matrix -> smem tile [64][pitch] (zero-filled past `rows` / hd)
-__device__ __forceinline__ void bwd_load_tile(__nv_bfloat16* dst, int pitch, const __nv_bfloat16* src, long long stride,
-                                              int row0, int rows, int hd, int hd_pad) {
-  const int wpr = hd_pad / 2;   // 32-bit words per staged row
-  for (int idx = threadIdx.x; idx < kBwdBM * wpr; idx += kBwdThreads) {
-    const int r = idx / wpr, w = idx - r * wpr;
-    uint32_t val = 0u;
-    if (row0 + r < rows && 2 * w < hd) val = *reinterpret_cast<const uint32_t*>(src + (long long)(row0 + r) * stride + 2 * w);
-    *reinterpret_cast<uint32_t*>(dst + r * pitch + 2 * w) = val;
+// rows [row0, row0 + 64) x hd of a row-strided bf16 matrix -> smem tile [64][KS * 16 + 8], asynchronously: cp.async copies
+// (16-byte when the source allows, else 4-byte), zero-filled past `rows` / hd.  The caller commits and waits.
+// (The first version staged tiles with a loop of dependent 32-bit load / store pairs: ~11 K clk per tile, every tile,
+// with nothing else running in the CTA — the dK/dV kernel spent 37 K clk per (query block, key block) pair.)
+template <int KS>
+__device__ __forceinline__ void bwd_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long stride, int row0,
+                                               int rows, int hd, int vec16) {
+  constexpr int pitch = KS * 16 + 8;
+  if (vec16) {
+    constexpr int cpr = KS * 2;   // 16-byte chunks per row
+#pragma unroll
+    for (int m = 0; m < (kBwdBM * cpr) / kBwdThreads; ++m) {
+      const int idx = (int)threadIdx.x + m * kBwdThreads;
+      const int r = idx / cpr, c = idx - r * cpr;
+      int bytes = (hd - c * 8) * 2;
+      bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+      if (row0 + r >= rows) bytes = 0;
+      const __nv_bfloat16* g = bytes ? src + (long long)(row0 + r) * stride + c * 8 : src;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst + r * pitch + c * 8)), "l"(g),
+                   "r"(bytes)
+                   : "memory");
+    }
+  } else {
+    constexpr int wpr = KS * 8;   // 32-bit words per row
+#pragma unroll 4
+    for (int m = 0; m < (kBwdBM * wpr) / kBwdThreads; ++m) {
+      const int idx = (int)threadIdx.x + m * kBwdThreads;
+      const int r = idx / wpr, w = idx - r * wpr;
+      const int bytes = (row0 + r < rows && 2 * w < hd) ? 4 : 0;
+      const __nv_bfloat16* g = bytes ? src + (long long)(row0 + r) * stride + 2 * w : src;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(dst + r * pitch + 2 * w)), "l"(g),
+                   "r"(bytes)
+                   : "memory");
+    }
   }
 }
 
@@ -89,16 +122,17 @@ __device__ __forceinline__ void bwd_row_range(const MaskParams& mp, int i, int* 
 
 // ---------------------------------------------------------------------------------------------------- dQ (+ lse, D)
 template <int KS>   // KS = hd_pad / 16
-__global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParams P) {
+__global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_kernel(const BwdParams P) {
   using namespace ptx;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   const PrefillParams& a = P.a;
   const int pitch = P.hd_pad + 8;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
-  __nv_bfloat16* sdO = sQ + kBwdBM * pitch;
-  __nv_bfloat16* sK = sdO + kBwdBM * pitch;
-  __nv_bfloat16* sV = sK + kBwdBM * pitch;
-  float* sD = reinterpret_cast<float*>(sV + kBwdBM * pitch);
+  // four tile buffers: Q / dO / O while the A fragments and D are taken, then K (pass 1) or K / V pairs (pass 2),
+  // double-buffered: the next KV block is on its way (cp.async) while the current one is computed on
+  auto sT = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(bwd_smem) + i * kBwdBM * pitch; };
+  __nv_bfloat16* sQ = sT(0);
+  __nv_bfloat16* sdO = sT(1);
+  float* sD = reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(bwd_smem) + 6 * kBwdBM * pitch);
 
   const int q0 = blockIdx.x * kBwdBM, h = blockIdx.y, n = blockIdx.z;
   const int g = h / a.hpg;
@@ -110,14 +144,16 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParam
   const __nv_bfloat16* vp = a.v + n * a.vs_n + (long long)g * a.vs_h;
 
   // ---- Q, dO (and O, parked in the K buffer) -> smem;  D_i = sum_c dO_ic * O_ic
-  bwd_load_tile(sQ, pitch, qp, a.qs_t, q0, a.Tq, a.hd, P.hd_pad);
-  bwd_load_tile(sdO, pitch, dop, P.dos_t, q0, a.Tq, a.hd, P.hd_pad);
-  bwd_load_tile(sK, pitch, op, a.os_t, q0, a.Tq, a.hd, P.hd_pad);
+  bwd_tile_async<KS>(sQ, qp, a.qs_t, q0, a.Tq, a.hd, P.vec16);
+  bwd_tile_async<KS>(sdO, dop, P.dos_t, q0, a.Tq, a.hd, P.vec16);
+  bwd_tile_async<KS>(sT(2), op, a.os_t, q0, a.Tq, a.hd, P.vec16);
+  cpasync_commit();
+  cpasync_wait<0>();
   __syncthreads();
   {
     const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
     float acc = 0.f;
-    for (int c = half; c < P.hd_pad; c += 2) acc += __bfloat162float(sdO[r * pitch + c]) * __bfloat162float(sK[r * pitch + c]);
+    for (int c = half; c < P.hd_pad; c += 2) acc += __bfloat162float(sdO[r * pitch + c]) * __bfloat162float(sT(2)[r * pitch + c]);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if (half == 0) sD[r] = acc;
   }
@@ -142,7 +178,7 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParam
   tile_range(a.mask, q0, kBwdBM, kBwdBN, &t_first, &t_last);
 
   // S[16 x 64] of this warp for the KV block in sK, scaled to log2 units and masked (-inf)
-  auto scores = [&](int k0, float (&s)[8][4]) {
+  auto scores = [&](const __nv_bfloat16* sK, int k0, float (&s)[8][4]) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
@@ -170,12 +206,16 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParam
 
   // ---- pass 1: row statistics (online max / sum over the visited KV blocks)
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int t = t_first; t <= t_last; ++t) {
-    __syncthreads();
-    bwd_load_tile(sK, pitch, kp, a.ks_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
-    __syncthreads();
+  __syncthreads();   // every warp holds its Q / dO fragments and D: the four buffers are free
+  if (t_first <= t_last) bwd_tile_async<KS>(sT(0), kp, a.ks_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+  cpasync_commit();
+  for (int t = t_first, it = 0; t <= t_last; ++t, ++it) {
+    cpasync_wait<0>();
+    __syncthreads();   // block t has landed for everyone, and everyone is done with block t - 1
+    if (t < t_last) bwd_tile_async<KS>(sT((it + 1) & 1), kp, a.ks_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+    cpasync_commit();
     float s[8][4];
-    scores(t * kBwdBN, s);
+    scores(sT(it & 1), t * kBwdBN, s);
     float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -221,13 +261,24 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParam
   float dq[KS * 2][4];
 #pragma unroll
   for (int nt = 0; nt < KS * 2; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
-  for (int t = t_first; t <= t_last; ++t) {
+  __syncthreads();   // pass 1 is done with its last block
+  if (t_first <= t_last) {
+    bwd_tile_async<KS>(sT(0), kp, a.ks_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+    bwd_tile_async<KS>(sT(1), vp, a.vs_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+  }
+  cpasync_commit();
+  for (int t = t_first, it = 0; t <= t_last; ++t, ++it) {
+    cpasync_wait<0>();
     __syncthreads();
-    bwd_load_tile(sK, pitch, kp, a.ks_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
-    bwd_load_tile(sV, pitch, vp, a.vs_t, t * kBwdBN, a.Tk, a.hd, P.hd_pad);
-    __syncthreads();
+    if (t < t_last) {
+      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1)), kp, a.ks_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1) + 1), vp, a.vs_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+    }
+    cpasync_commit();
+    const __nv_bfloat16* sK = sT(2 * (it & 1));
+    const __nv_bfloat16* sV = sT(2 * (it & 1) + 1);
     float s[8][4];
-    scores(t * kBwdBN, s);
+    scores(sK, t * kBwdBN, s);
     float dp[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
@@ -286,24 +337,24 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dq_kernel(const BwdParam
 
 // ---------------------------------------------------------------------------------------------------- dK, dV
 template <int KS>
-__global__ void __launch_bounds__(kBwdThreads) attn_bwd_dkv_kernel(const BwdParams P) {
+__global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dkv_kernel(const BwdParams P) {
   using namespace ptx;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   const PrefillParams& a = P.a;
   const int pitch = P.hd_pad + 8;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
-  __nv_bfloat16* sdO = sQ + kBwdBM * pitch;
-  __nv_bfloat16* sK = sdO + kBwdBM * pitch;
-  __nv_bfloat16* sV = sK + kBwdBM * pitch;
-  float* sLse = reinterpret_cast<float*>(sV + kBwdBM * pitch);
-  float* sD = sLse + kBwdBM;
+  // six tile buffers: K, V of this block (resident) and two Q / dO pairs — the next (head, query block) pair is on its
+  // way (cp.async) while the current one is computed on; its lse / D rows travel through registers
+  __nv_bfloat16* sT0 = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
+  __nv_bfloat16* sK = sT0;
+  __nv_bfloat16* sV = sT0 + kBwdBM * pitch;
+  float* sStat = reinterpret_cast<float*>(sT0 + 6 * kBwdBM * pitch);   // [2 buffers][lse | D][64]
 
   const int k0 = blockIdx.x * kBwdBN, g = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
   const __nv_bfloat16* kp = a.k + n * a.ks_n + (long long)g * a.ks_h;
   const __nv_bfloat16* vp = a.v + n * a.vs_n + (long long)g * a.vs_h;
-  bwd_load_tile(sK, pitch, kp, a.ks_t, k0, a.Tk, a.hd, P.hd_pad);
-  bwd_load_tile(sV, pitch, vp, a.vs_t, k0, a.Tk, a.hd, P.hd_pad);
+  bwd_tile_async<KS>(sK, kp, a.ks_t, k0, a.Tk, a.hd, P.vec16);
+  bwd_tile_async<KS>(sV, vp, a.vs_t, k0, a.Tk, a.hd, P.vec16);
 
   // this thread's two key rows
   const int j0 = k0 + warp * 16 + gq, j1 = j0 + 8;
@@ -319,25 +370,57 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dkv_kernel(const BwdPara
   }
 
   const int q_blocks = (a.Tq + kBwdBM - 1) / kBwdBM;
-  for (int hh = 0; hh < a.hpg; ++hh) {
-    const int h = g * a.hpg + hh;
-    const __nv_bfloat16* qp = a.q + n * a.qs_n + (long long)h * a.qs_h;
-    const __nv_bfloat16* dop = P.dout + n * P.dos_n + (long long)h * P.dos_h;
-    for (int qb = 0; qb < q_blocks; ++qb) {
-      const int q0 = qb * kBwdBM;
-      int t_first, t_last;
-      tile_range(a.mask, q0, kBwdBM, kBwdBN, &t_first, &t_last);
-      if ((int)blockIdx.x < t_first || (int)blockIdx.x > t_last) continue;   // no (query, key) pair of the two blocks is allowed
-      __syncthreads();
-      bwd_load_tile(sQ, pitch, qp, a.qs_t, q0, a.Tq, a.hd, P.hd_pad);
-      bwd_load_tile(sdO, pitch, dop, P.dos_t, q0, a.Tq, a.hd, P.hd_pad);
-      if (threadIdx.x < kBwdBM) {
-        const int i = q0 + threadIdx.x;
-        const bool live = i < a.Tq && (a.q_valid == nullptr || a.q_valid[(long long)n * a.Tq + i]);
-        sLse[threadIdx.x] = live ? P.lse[((long long)n * a.H + h) * a.Tq + i] : INFINITY;
-        sD[threadIdx.x] = live ? P.dsum[((long long)n * a.H + h) * a.Tq + i] : 0.f;
+  // the (head of the group, query block) pairs with at least one allowed (query, key) pair against this key block, in
+  // order; `advance` moves to the next one (every thread walks the same sequence)
+  auto advance = [&](int& hh, int& qb) -> bool {
+    for (;;) {
+      if (++qb >= q_blocks) {
+        qb = 0;
+        if (++hh >= a.hpg) return false;
       }
-      __syncthreads();
+      int t_first, t_last;
+      tile_range(a.mask, qb * kBwdBM, kBwdBM, kBwdBN, &t_first, &t_last);
+      if ((int)blockIdx.x >= t_first && (int)blockIdx.x <= t_last) return true;
+    }
+  };
+  auto stage_pair = [&](int hh, int qb, int buf) {
+    const int h = g * a.hpg + hh;
+    bwd_tile_async<KS>(sT0 + (2 + 2 * buf) * kBwdBM * pitch, a.q + n * a.qs_n + (long long)h * a.qs_h, a.qs_t,
+                       qb * kBwdBM, a.Tq, a.hd, P.vec16);
+    bwd_tile_async<KS>(sT0 + (3 + 2 * buf) * kBwdBM * pitch, P.dout + n * P.dos_n + (long long)h * P.dos_h, P.dos_t,
+                       qb * kBwdBM, a.Tq, a.hd, P.vec16);
+  };
+  auto load_stats = [&](int hh, int qb, float* lse, float* dsum) {   // threads < 64: row threadIdx.x of the query block
+    const int h = g * a.hpg + hh;
+    const int i = qb * kBwdBM + (int)threadIdx.x;
+    const bool live = i < a.Tq && (a.q_valid == nullptr || a.q_valid[(long long)n * a.Tq + i]);
+    *lse = live ? P.lse[((long long)n * a.H + h) * a.Tq + i] : INFINITY;
+    *dsum = live ? P.dsum[((long long)n * a.H + h) * a.Tq + i] : 0.f;
+  };
+  int hh = 0, qb = -1;
+  bool have = advance(hh, qb);
+  if (have) {
+    stage_pair(hh, qb, 0);
+    if (threadIdx.x < kBwdBM) load_stats(hh, qb, &sStat[threadIdx.x], &sStat[kBwdBM + threadIdx.x]);
+  }
+  cpasync_commit();
+  for (int it = 0; have; ++it) {
+    int nh = hh, nq = qb;
+    const bool more = advance(nh, nq);
+    cpasync_wait<0>();
+    __syncthreads();   // this pair (and K, V) has landed for everyone, and everyone is done with the previous pair
+    float lse_n = INFINITY, dsum_n = 0.f;
+    if (more) {
+      stage_pair(nh, nq, (it + 1) & 1);
+      if (threadIdx.x < kBwdBM) load_stats(nh, nq, &lse_n, &dsum_n);
+    }
+    cpasync_commit();
+    const __nv_bfloat16* sQ = sT0 + (2 + 2 * (it & 1)) * kBwdBM * pitch;
+    const __nv_bfloat16* sdO = sT0 + (3 + 2 * (it & 1)) * kBwdBM * pitch;
+    const float* sLse = sStat + (it & 1) * 2 * kBwdBM;
+    const float* sD = sLse + kBwdBM;
+    const int q0 = qb * kBwdBM;
+    {
 
       // ---- S^T = K Q^T for this warp's 16 keys x 64 queries, then P^T (rows = keys j0 / j1, columns = queries)
       float st[8][4];
@@ -426,7 +509,15 @@ __global__ void __launch_bounds__(kBwdThreads) attn_bwd_dkv_kernel(const BwdPara
         }
       }
     }
+    if (more && threadIdx.x < kBwdBM) {   // (the other stat buffer was last read two pairs ago)
+      sStat[((it + 1) & 1) * 2 * kBwdBM + threadIdx.x] = lse_n;
+      sStat[((it + 1) & 1) * 2 * kBwdBM + kBwdBM + threadIdx.x] = dsum_n;
+    }
+    hh = nh;
+    qb = nq;
+    have = more;
   }
+  cpasync_wait<0>();   // (a block without any pair still staged its K / V)
   // ---- bf16 outputs (dense [N, Tk, G, hd])
   __nv_bfloat16* dkp = P.dk + (((long long)n * a.Tk) * a.G + g) * a.hd;
   __nv_bfloat16* dvp = P.dv + (((long long)n * a.Tk) * a.G + g) * a.hd;

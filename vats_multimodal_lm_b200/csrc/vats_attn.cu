@@ -1098,6 +1098,12 @@ int vats_attn_prefill_backward(const void* q, const void* k, const void* v, cons
   P.dsum = P.lse + (size_t)N * H * Tq;
   P.scale = scale;
   P.hd_pad = (hd + 15) / 16 * 16;
+  {
+    auto al16 = [&](const void* ptr, const int64_t* st3) {
+      return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && st3[0] % 8 == 0 && st3[1] % 8 == 0 && st3[2] % 8 == 0;
+    };
+    P.vec16 = (al16(A.q, A.qs) && al16(A.k, A.ks) && al16(A.v, A.vs) && al16(A.o, A.os) && al16(dout, do_strides)) ? 1 : 0;
+  }
   const size_t smem = vats::bwd_smem_bytes(P.hd_pad);
   const int ks = P.hd_pad / 16;
   const dim3 grid_q((Tq + vats::kBwdBM - 1) / vats::kBwdBM, H, N);
