@@ -27,6 +27,9 @@
 
 namespace vats {
 
+#ifndef VATS_BWD_DQ_FAST   // A/B knob: unmasked fast path of the dQ kernel's score tile
+#define VATS_BWD_DQ_FAST 1
+#endif
 #ifndef VATS_BWD_OCC   // A/B knob: 1 = ask ptxas for 3 CTAs per SM up to head dim 64 (2 up to 96)
 #define VATS_BWD_OCC 1
 #endif
@@ -63,31 +66,38 @@ template <int KS>
 __device__ __forceinline__ void bwd_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long stride, int row0,
                                                int rows, int hd, int vec16) {
   constexpr int pitch = KS * 16 + 8;
-  if (vec16) {
-    constexpr int cpr = KS * 2;   // 16-byte chunks per row
+  constexpr int cpr = KS * 2;            // 16-byte chunks per row
+  constexpr int segs = (cpr + 7) / 8;    // 128-byte segments per row
+  // Eight consecutive threads take the eight 16-byte chunks of one 128-byte row segment (one line per row and warp
+  // instruction, conflict-free shared-memory writes); a thread's rows are tid / 8 + 16 m, so it computes one address
+  // per tile and steps it by 16 rows.  (A division of the chunk index per copy made the address arithmetic a fifth of
+  // all executed instructions; two threads per row with interleaved chunks quadrupled the L2 requests.)
+  const int rb = (int)threadIdx.x >> 3, c0 = (int)threadIdx.x & 7;
+  const __nv_bfloat16* g = src + (long long)(row0 + rb) * stride + c0 * 8;
+  const uint32_t d = ptx::smem_u32(dst + rb * pitch + c0 * 8);
 #pragma unroll
-    for (int m = 0; m < (kBwdBM * cpr) / kBwdThreads; ++m) {
-      const int idx = (int)threadIdx.x + m * kBwdThreads;
-      const int r = idx / cpr, c = idx - r * cpr;
-      int bytes = (hd - c * 8) * 2;
-      bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-      if (row0 + r >= rows) bytes = 0;
-      const __nv_bfloat16* g = bytes ? src + (long long)(row0 + r) * stride + c * 8 : src;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst + r * pitch + c * 8)), "l"(g),
-                   "r"(bytes)
-                   : "memory");
-    }
-  } else {
-    constexpr int wpr = KS * 8;   // 32-bit words per row
-#pragma unroll 4
-    for (int m = 0; m < (kBwdBM * wpr) / kBwdThreads; ++m) {
-      const int idx = (int)threadIdx.x + m * kBwdThreads;
-      const int r = idx / wpr, w = idx - r * wpr;
-      const int bytes = (row0 + r < rows && 2 * w < hd) ? 4 : 0;
-      const __nv_bfloat16* g = bytes ? src + (long long)(row0 + r) * stride + 2 * w : src;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(dst + r * pitch + 2 * w)), "l"(g),
-                   "r"(bytes)
-                   : "memory");
+  for (int m = 0; m < kBwdBM / 16; ++m) {
+    const bool live = row0 + rb + 16 * m < rows;
+#pragma unroll
+    for (int sg = 0; sg < segs; ++sg) {
+      const int c = c0 + 8 * sg;
+      if (cpr % 8 == 0 || c < cpr) {
+        if (vec16) {
+          int bytes = (hd - c * 8) * 2;
+          bytes = !live ? 0 : (bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (m * 16 * pitch + sg * 64) * 2),
+                       "l"(bytes ? g + (long long)(16 * m) * stride + sg * 64 : src), "r"(bytes)
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {   // the same chunk as four 32-bit copies (rows only 4-byte aligned)
+            const int bytes = (live && c * 8 + 2 * w < hd) ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + (m * 16 * pitch + sg * 64) * 2 + w * 4),
+                         "l"(bytes ? g + (long long)(16 * m) * stride + sg * 64 + 2 * w : src), "r"(bytes)
+                         : "memory");
+          }
+        }
+      }
     }
   }
 }
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
   using namespace ptx;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   const PrefillParams& a = P.a;
-  const int pitch = P.hd_pad + 8;
+  constexpr int pitch = KS * 16 + 8;   // == P.hd_pad + 8: compile-time, so fragment addresses fold into constants
   // four tile buffers: Q / dO / O while the A fragments and D are taken, then K (pass 1) or K / V pairs (pass 2),
   // double-buffered: the next KV block is on its way (cp.async) while the current one is computed on
   auto sT = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(bwd_smem) + i * kBwdBM * pitch; };
@@ -177,6 +187,8 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
   int t_first, t_last;
   tile_range(a.mask, q0, kBwdBM, kBwdBN, &t_first, &t_last);
 
+  // all 64 rows of the block are live and no key mask: blocks the geometry allows entirely need no predicate
+  const bool plain_rows = a.q_valid == nullptr && a.k_valid == nullptr && q0 + kBwdBM <= a.Tq;
   // S[16 x 64] of this warp for the KV block in sK, scaled to log2 units and masked (-inf)
   auto scores = [&](const __nv_bfloat16* sK, int k0, float (&s)[8][4]) {
 #pragma unroll
@@ -190,6 +202,14 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
         mma_bf16_16816(s[np * 2], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[0], b[1]);
         mma_bf16_16816(s[np * 2 + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[2], b[3]);
       }
+    }
+    if (VATS_BWD_DQ_FAST && plain_rows && tile_is_full(a.mask, k0 / kBwdBN, q0, kBwdBM, kBwdBN)) {   // every pair allowed
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nt][e] *= a.scale_log2;
+      }
+      return;
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dkv_
   using namespace ptx;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   const PrefillParams& a = P.a;
-  const int pitch = P.hd_pad + 8;
+  constexpr int pitch = KS * 16 + 8;   // == P.hd_pad + 8: compile-time, so fragment addresses fold into constants
   // six tile buffers: K, V of this block (resident) and two Q / dO pairs — the next (head, query block) pair is on its
   // way (cp.async) while the current one is computed on; its lse / D rows travel through registers
   __nv_bfloat16* sT0 = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
@@ -438,17 +458,31 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dkv_
           mma_bf16_16816(st[np * 2 + 1], ka[0], ka[1], ka[2], ka[3], bq[2], bq[3]);
         }
       }
+      // allowed query columns (local index il) of this thread's two key rows, from the predicate solved for i:
+      //   causal: j <= i + off  <=>  il >= j - off - q0;   right: il >= j - right - off - q0;   left: il <= j + left - off - q0
+      int ilo0 = 0, ihi0 = kBwdBM - 1, ilo1 = 0, ihi1 = kBwdBM - 1;
+      if (!tile_is_full(a.mask, (int)blockIdx.x, q0, kBwdBM, kBwdBN)) {
+        const long long base = off + (long long)q0;
+        auto clampi = [](long long x) { return x < -1 ? -1 : (x > kBwdBM ? kBwdBM : (int)x); };
+        long long l0 = 0, l1 = 0, h0 = kBwdBM - 1, h1 = kBwdBM - 1;
+        if (a.mask.causal) { l0 = (long long)j0 - base; l1 = (long long)j1 - base; }
+        if (a.mask.right >= 0) {
+          const long long r0 = (long long)j0 - a.mask.right - base, r1 = (long long)j1 - a.mask.right - base;
+          l0 = (a.mask.causal && l0 > r0) ? l0 : r0;
+          l1 = (a.mask.causal && l1 > r1) ? l1 : r1;
+        }
+        if (a.mask.left >= 0) { h0 = (long long)j0 + a.mask.left - base; h1 = (long long)j1 + a.mask.left - base; }
+        ilo0 = clampi(l0 < 0 ? 0 : l0); ilo1 = clampi(l1 < 0 ? 0 : l1);
+        ihi0 = clampi(h0 > kBwdBM - 1 ? kBwdBM - 1 : h0); ihi1 = clampi(h1 > kBwdBM - 1 ? kBwdBM - 1 : h1);
+      }
+      if (!kv0) ihi0 = -1;   // key row past the sequence or masked by k_valid
+      if (!kv1) ihi1 = -1;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int il = nt * 8 + tq * 2 + (e & 1);      // query column within the block
-          const long long ii = (long long)(q0 + il) + off;
-          const int j = e < 2 ? j0 : j1;
-          bool ok = e < 2 ? kv0 : kv1;
-          if (a.mask.causal && (long long)j > ii) ok = false;
-          if (a.mask.left >= 0 && (long long)j < ii - a.mask.left) ok = false;
-          if (a.mask.right >= 0 && (long long)j > ii + a.mask.right) ok = false;
+          const bool ok = e < 2 ? (il >= ilo0 && il <= ihi0) : (il >= ilo1 && il <= ihi1);
           st[nt][e] = ok ? ex2(st[nt][e] * a.scale_log2 - sLse[il]) : 0.f;   // lse = +inf for dead / padded rows
         }
       }
