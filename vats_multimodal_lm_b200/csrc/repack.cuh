@@ -2,8 +2,9 @@
 // views) into a TMA-addressable layout: head stride rounded up to 8 elements, token / sequence strides dense.
 //
 // The tcgen05 kernel can stage such tensors itself (cp.async variant), but its 96 loader threads issue one 4-byte
-// copy per element pair and become the limit (cfg4a: 2.5 ms).  One streaming pass at HBM speed plus the TMA-fed kernel
-// is faster (cfg4a: 0.25 + 1.1 ms), which is also what the drop-in modules do when they cast to bf16.
+// copy per element pair and become the limit (cfg4a: 2.0 ms).  One streaming pass at HBM speed plus the TMA-fed kernel
+// is faster (cfg4a: 0.20 + 0.43 ms with repack_chunk_kernel and the resident-K/V kernel), which is also what the
+// drop-in modules do when they cast to bf16.
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>

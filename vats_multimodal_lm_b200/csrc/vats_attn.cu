@@ -686,7 +686,7 @@ int launch_mid(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
   P.num_items = A.N * A.G;
   if (any_ldg) {
     // rows TMA cannot address (dense hd 66 / 60): with caller-owned scratch, one streaming repack + the TMA-fed
-    // kernel (cfg4a dense: 0.25 + 0.53 ms) beats the in-kernel cp.async staging (2.0 ms: 96 loader threads issuing
+    // kernel (cfg4a dense: 0.20 + 0.43 ms) beats the in-kernel cp.async staging (2.0 ms: 96 loader threads issuing
     // 4-byte copies with per-copy address arithmetic)
     const int rc2 = launch_tc_repacked(A, pl, st, /*mid=*/true);
     if (rc2 >= 0) return rc2;
