@@ -756,6 +756,74 @@ def bench_backward(c, peaks, steps, rank):
                      "autograd dispatch")
 
 
+MODULE_LAYERS = [
+    # name, builder, input shape, forward kwargs — the drop-in attention modules at the BASELINE geometries, bf16 weights
+    dict(name="layer_cfg1_llm_attention_T4096", kind="llm", d_model=1440, H=24, G=8, shape=(1, 4096, 1440)),
+    dict(name="layer_cfg3_vit2d_spatial_attention", kind="vit2d", d_model=1152, H=16, G=8, shape=(256, 196, 1152)),
+    dict(name="layer_cfg4_vit3d_spatiotemporal_attention", kind="vit3d", d_model=2112, H=32, G=8, shape=(64, 8, 196, 2112)),
+]
+
+
+def bench_module_layer(c, steps, rank):
+    """One forward of a drop-in attention module (projection GEMMs in torch + producers + core + output projection),
+    inference mode, twice: with the fused producer kernels (qk-norm + RoPE + bf16 cast + kernel layout in one launch,
+    SURVEY §8f ranks 1-2) and with the PyTorch element-wise passes the modules use under autograd.  Same weights, same
+    input; the outputs of the two paths are compared."""
+    import vats_multimodal_lm_b200 as vl
+    from vats_multimodal_lm_b200 import _ffi
+    from vats_multimodal_lm_b200.modules import llm as L, vit2d as V2, vit3d as V3
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(4321 + rank)
+    hd = c["d_model"] // c["H"]
+    if c["kind"] == "llm":
+        m = vl.Attention(c["d_model"], c["H"], c["G"], 10000.0, hd ** -0.5)
+        call = lambda x: m(x, 384, 0, True, None, None, None, False, False, True)[0]
+    elif c["kind"] == "vit2d":
+        m = vl.SpatialAttention(c["d_model"], c["H"], c["G"], 10000.0, 224, 16, hd ** -0.5, False, False, True)
+        call = lambda x: m(x, False, True, -1, -1)
+    else:
+        m = vl.SpatioTemporalAttention(c["d_model"], c["H"], c["G"], 10000.0, (2, 16, 16))
+        call = lambda x: m(x, (c["shape"][1], 14, 14), False, True, None, None)
+    m = m.to(dev).bfloat16().eval()
+    x = (torch.randn(c["shape"], device=dev) * 0.5).bfloat16()
+    mods = (L, V2, V3)
+    saved = [mod._on_gpu for mod in mods]
+
+    def timed(fused):
+        for mod, orig in zip(mods, saved):
+            mod._on_gpu = orig if fused else (lambda t: False)
+        try:
+            with torch.no_grad():
+                for _ in range(3):
+                    y = call(x)
+                torch.cuda.synchronize()
+                kernel = _ffi.last_kernel()
+                evs = []
+                for _ in range(steps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    y = call(x)
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+            return statistics.mean(a.elapsed_time(b) for a, b in evs), y, kernel
+        finally:
+            for mod, orig in zip(mods, saved):
+                mod._on_gpu = orig
+
+    ms_fused, y_fused, kernel = timed(True)
+    ms_plain, y_plain, _ = timed(False)
+    d = (y_fused.float() - y_plain.float())
+    return dict(ms_layer_fused_producers=ms_fused, ms_layer_pytorch_producers=ms_plain, iterations=steps,
+                core_kernel=kernel, tokens=int(x.numel() // c["d_model"]),
+                tokens_per_s=int(x.numel() // c["d_model"]) / (ms_fused * 1e-3),
+                fused_vs_pytorch_path=dict(max_abs=d.abs().max().item(),
+                                           rel_l2=(d.norm() / y_plain.float().norm()).item()),
+                note="whole module forward incl. the torch projection GEMMs (bf16 weights); the two timings differ only "
+                     "in how q / k / v get from the projection to the core: one producer launch vs ~12 element-wise "
+                     "passes + cast / layout copies")
+
+
 def cpu_baseline_decode():
     """Oracle-side port of the reference CPU path on a bounded sample, rank 0 / N=1 only."""
     from oracle.cpu_baseline import reference_decode_cpu, time_callable
@@ -811,6 +879,15 @@ def run_ours(args):
                 other[TRAIN_CFG["name"]] = bench_backward(TRAIN_CFG, peaks, 20, rank)
             except Exception as e:
                 other[TRAIN_CFG["name"]] = {"error": f"{type(e).__name__}: {e}"}
+            # whole-module forwards run in a child process: whatever happens there cannot take the headline line down
+            torch.cuda.empty_cache()
+            try:
+                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--layers-only"], capture_output=True,
+                                    text=True, timeout=420)
+                layers = json.loads(cp.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                layers = {lc["name"]: {"error": f"{type(e).__name__}: {e}"} for lc in MODULE_LAYERS}
+            other.update(layers)
     cpu = None
     if rank == 0 and world == 1:
         try:
@@ -861,6 +938,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--layers-only", action="store_true", help="(internal) time the whole-module forwards, print a JSON dict")
     ap.add_argument("--cache-layout", default="bshd", choices=["bshd", "bhsd"],
                     help="storage order of the KV cache behind its [B,S,G,hd] shape")
     args = ap.parse_args()
@@ -870,7 +948,17 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    if args.impl == "reference":
+    if args.layers_only:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        res = {}
+        for lc in MODULE_LAYERS:
+            try:
+                res[lc["name"]] = bench_module_layer(lc, 10, 0)
+            except Exception as e:
+                res[lc["name"]] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        emit(res)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -5,6 +5,9 @@ print(f"decode: value={d['value']:.0f} GB/s achieved={r['achieved']:.0f} ({100*r
 for k, v in d.get("other_workloads", {}).items():
     if "error" in v:
         print(k, "ERROR", v["error"]); continue
+    if "ms_layer_fused_producers" in v:
+        print(f"{k:26s} fused {v['ms_layer_fused_producers']:.4f} ms  pytorch producers {v['ms_layer_pytorch_producers']:.4f} ms  diff {v['fused_vs_pytorch_path']}")
+        continue
     if "ms_forward" in v:
         print(f"{k:26s} fwd {v['ms_forward']:.4f} ms ({v['tflops_forward']:.1f} TFLOP/s)  bwd {v['ms_backward']:.4f} ms ({v['tflops_backward']:.1f} TFLOP/s)")
         continue
