@@ -59,8 +59,6 @@ extern "C" {
 #define VATS_KERNEL_TCGEN05 1 /* TMA + tcgen05/TMEM tile kernel; error if the geometry is not TMA-legal */
 #define VATS_KERNEL_SIMT 2    /* CUDA-core warp kernel for tiny / irregular sequences */
 #define VATS_KERNEL_MID 3     /* tcgen05 kernel for <= 256 keys: K/V of a KV group resident in shared memory */
-#define VATS_KERNEL_TC64 4    /* the tile kernel with 64-key steps and double-buffered S (what AUTO takes for long KV loops
-                                 on TMA-addressable tensors); error if the tensors are not TMA-addressable */
 
 /*
  * Prefill / encoder attention:  O[n,i,h,:] = softmax_j( scale * <Q[n,i,h,:], K[n,j,h/(H/G),:]> | allowed ) . V[n,j,h/(H/G),:]
@@ -259,7 +257,6 @@ int vats_attn_last_launch_count(void);
 #define VATS_LAUNCHED_DECODE_PREPARE 8
 #define VATS_LAUNCHED_PREFILL_MID 9      /* prefill_mid_kernel: 33..256 keys, K/V resident per (sequence, KV group) */
 #define VATS_LAUNCHED_BACKWARD 10        /* attention backward kernels */
-#define VATS_LAUNCHED_PREFILL_TC64 11    /* prefill_tc64_kernel: 64-key steps, double-buffered S (long sequences) */
 int vats_attn_last_kernel(void);
 
 /*

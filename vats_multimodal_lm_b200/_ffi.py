@@ -19,7 +19,6 @@ KERNEL_AUTO = 0
 KERNEL_TCGEN05 = 1
 KERNEL_SIMT = 2
 KERNEL_MID = 3
-KERNEL_TC64 = 4
 
 # every symbol include/vats_attn.h declares (tests check that the library exports exactly these)
 EXPORTED_SYMBOLS = (
@@ -168,7 +167,7 @@ def last_launch_count() -> int:
 
 
 LAUNCHED = {0: "none", 1: "prefill_tc", 2: "prefill_tc_ldg", 3: "prefill_short", 4: "prefill_simt", 5: "decode_mma",
-            6: "decode_split", 7: "prefill_prepare", 8: "decode_prepare", 9: "prefill_mid", 10: "backward", 11: "prefill_tc64"}
+            6: "decode_split", 7: "prefill_prepare", 8: "decode_prepare", 9: "prefill_mid", 10: "backward"}
 
 
 def last_kernel() -> str:

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["vats_attn.cu"]
-HEADERS = ["ptx.cuh", "mask.cuh", "decode.cuh", "prefill_simt.cuh", "prefill_tc.cuh", "prefill_tc64.cuh", "prefill_short.cuh", "prefill_mid.cuh", "decode_mma.cuh", "decode_prepare.cuh", "repack.cuh", "backward.cuh",
+HEADERS = ["ptx.cuh", "mask.cuh", "decode.cuh", "prefill_simt.cuh", "prefill_tc.cuh", "prefill_short.cuh", "prefill_mid.cuh", "decode_mma.cuh", "decode_prepare.cuh", "repack.cuh", "backward.cuh",
            os.path.join("..", "..", "include", "vats_attn.h")]
 # VATS_BUILD_OUT: build a variant (e.g. VATS_ENABLE_TRACE=1) next to the product library instead of over it
 OUT = os.environ.get("VATS_BUILD_OUT") or os.path.join(CSRC, "libvats_attn.so")

@@ -20,7 +20,6 @@
 #include "mask.cuh"
 #include "prefill_simt.cuh"
 #include "prefill_tc.cuh"
-#include "prefill_tc64.cuh"
 #include "prefill_short.cuh"
 #include "prefill_mid.cuh"
 #include "decode_prepare.cuh"
@@ -32,7 +31,6 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_last_kernel = 0;   // VATS_LAUNCHED_* of the last successful launch on this thread
-thread_local bool g_auto_choice = false;   // the running call was made with VATS_KERNEL_AUTO
 unsigned long long* g_trace = nullptr;  // debug timeline buffer (device memory), see vats_attn_debug_set_trace
 int g_trace_cap = 0;
 
@@ -501,73 +499,7 @@ int launch_tc_repacked(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st, 
   return rc;
 }
 
-// Long sequences on TMA-addressable tensors: the 64-key-step kernel with double-buffered S (prefill_tc64.cuh).  Returns
-// -1 when the launch does not qualify (the caller goes on with prefill_tc_kernel).
-int launch_tc64(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st, bool force = false) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("VATS_PREFILL_TC64");  // tuning knob: 0 = always the 128-key-step kernel, 1 = force on
-    enabled = e ? atoi(e) : 2;                    // 2 = by geometry
-  }
-  if ((enabled == 0 && !force) || A.world > 0) return -1;
-  if (pl.q != LoadMode::kTma || pl.k != LoadMode::kTma || pl.v != LoadMode::kTma) return -1;
-  if (plan_load(A.o, A.hd, A.os) != LoadMode::kTma) return -1;
-  long long keys = A.Tk;   // keys a query block visits
-  if (A.left >= 0 && (A.causal || A.right >= 0)) {
-    const long long band = (long long)A.left + (A.causal ? 0 : A.right) + vats::kTcBlockM;
-    if (band < keys) keys = band;
-  }
-  if (enabled == 2 && !force && keys < 1024) return -1;   // short KV loops: the prologue / epilogue per item dominate either way
-  vats::TcParams P;
-  std::memset(&P, 0, sizeof(P));
-  fill_common(P.a, A);
-  P.hd_pad = (A.hd + 15) / 16 * 16;
-  P.regions = (P.hd_pad + 63) / 64;
-  P.q_blocks = (A.Tq + vats::kTcBlockM - 1) / vats::kTcBlockM;
-  P.pairs = (P.a.hpg + 1) / 2;
-  P.no_band = (!A.causal && A.left < 0 && A.right < 0) ? 1 : 0;
-  P.bounded = A.logit_bound > 0.f ? 1 : 0;
-  P.bound_log2 = bound_log2_of(A);
-  P.o_stage = 1;
-  const int q_bytes = 2 * P.regions * vats::kTcRegionBytes;
-  const int kv_bytes = P.regions * vats::kTc64RegionBytes;
-  const int budget = 227 * 1024 - 1024 - (int)sizeof(vats::Tc64Barriers) - q_bytes - 8 * vats::kTcOStageBytes;
-  int stages = budget / kv_bytes;
-  int nk = stages / 2, nv = stages - nk;
-  if (nk > vats::kTcMaxStages) nk = vats::kTcMaxStages;
-  if (nv > vats::kTcMaxStages) nv = vats::kTcMaxStages;
-  if (nk < 3 || nv < 2) return -1;   // S runs two steps ahead: the K ring needs three slots
-  P.nk = nk;
-  P.nv = nv;
-  const size_t smem = vats::tc64_smem_bytes(P.regions, nk, nv, 1);
-  CUtensorMap mq, mk, mv, mo;
-  int rc;
-  if ((rc = encode_map(&mq, A.q, A.N, A.Tq, A.H, A.hd, A.qs)) != VATS_OK) return rc;
-  if ((rc = encode_map(&mk, A.k, A.N, A.Tk, A.G, A.hd, A.ks, vats::kTc64BlockN)) != VATS_OK) return rc;
-  if ((rc = encode_map(&mv, A.v, A.N, A.Tk, A.G, A.hd, A.vs, vats::kTc64BlockN)) != VATS_OK) return rc;
-  if ((rc = encode_map(&mo, A.o, A.N, A.Tq, A.H, A.hd, A.os, 32)) != VATS_OK) return rc;
-  const long long ctas = (long long)A.N * A.G * P.pairs * P.q_blocks;
-  if (ctas > 0x7fffffffLL) return -1;
-  P.num_work = (int)ctas;
-  vats::tc_find_divisor((unsigned)P.q_blocks, P.div_qb);
-  vats::tc_find_divisor((unsigned)P.pairs, P.div_pairs);
-  vats::tc_find_divisor((unsigned)A.G, P.div_g);
-  int grid = sm_count();
-  if (grid > P.num_work) grid = P.num_work;
-  static thread_local SmemAttrCache smem_set;
-  CUDA_TRY(ensure_dyn_smem(vats::prefill_tc64_kernel, smem, smem_set));
-  vats::prefill_tc64_kernel<<<(unsigned)grid, vats::kTcThreads, smem, st>>>(P, mq, mk, mv, mo);
-  CUDA_TRY(cudaGetLastError());
-  g_launches = 1;
-  g_last_kernel = VATS_LAUNCHED_PREFILL_TC64;
-  return VATS_OK;
-}
-
 int launch_tc(const PrefillArgs& A, const TcPlan& pl, cudaStream_t st) {
-  if (g_auto_choice) {   // VATS_KERNEL_AUTO: long KV loops on TMA-addressable tensors take the 64-key-step kernel
-    const int rc64 = launch_tc64(A, pl, st);
-    if (rc64 >= 0) return rc64;
-  }
   vats::TcParams P;
   std::memset(&P, 0, sizeof(P));
   fill_common(P.a, A);
@@ -871,7 +803,6 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TcPlan pl{LoadMode::kNone, LoadMode::kNone, LoadMode::kNone};
   int auto_choice = choose_kernel(A, &pl);
-  g_auto_choice = kernel == VATS_KERNEL_AUTO;
   if (kernel == VATS_KERNEL_AUTO) {
     kernel = auto_choice;
     if (kernel == VATS_KERNEL_MID) {
@@ -887,14 +818,6 @@ int prefill_impl(const PrefillArgs& A, int kernel, void* stream) {
                   "4-byte aligned bases)",
                   A.hd);
     return launch_tc(A, pl, st);
-  }
-  if (kernel == VATS_KERNEL_TC64) {
-    if (tc_legal(A, &pl)) {
-      const int rc2 = launch_tc64(A, pl, st, /*force=*/true);
-      if (rc2 >= 0) return rc2;
-    }
-    return fail(VATS_ERR_UNSUPPORTED, "64-key-step tile kernel: needs TMA-addressable q / k / v / o (16-byte aligned bases "
-                                      "and strides, head_dim a multiple of 8) and room for three K stages (hd=%d)", A.hd);
   }
   if (kernel == VATS_KERNEL_MID) {
     if (!tc_legal(A, &pl) || !mid_legal(A, pl))

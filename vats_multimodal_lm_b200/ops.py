@@ -19,13 +19,12 @@ import torch
 
 from . import _ffi
 
-__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_bwd", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "prefill_prepare_table", "prefill_prepare_table_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID", "KERNEL_TC64"]
+__all__ = ["gqa_swa_prefill", "gqa_swa_prefill_bwd", "gqa_swa_prefill_gather", "gqa_swa_decode", "decode_prepare", "reset_decode_workspaces", "prefill_prepare", "prefill_prepare_views", "prefill_prepare_table", "prefill_prepare_table_views", "attn_mask", "KERNEL_AUTO", "KERNEL_TCGEN05", "KERNEL_SIMT", "KERNEL_MID"]
 
 KERNEL_AUTO = _ffi.KERNEL_AUTO
 KERNEL_TCGEN05 = _ffi.KERNEL_TCGEN05
 KERNEL_SIMT = _ffi.KERNEL_SIMT
 KERNEL_MID = _ffi.KERNEL_MID
-KERNEL_TC64 = _ffi.KERNEL_TC64
 
 
 def _require_cuda_bf16(name: str, t: torch.Tensor) -> None:
