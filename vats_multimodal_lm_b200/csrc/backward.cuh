@@ -11,9 +11,10 @@
 //
 // Two kernels, both bf16 operands / fp32 accumulation on mma.sync.m16n8k16 with operands staged in shared memory
 // (ldmatrix), deterministic (no atomics):
-//   attn_bwd_dq_kernel   one CTA per (sequence, query head, 64 query rows): recomputes the row statistics (the forward
-//                        kernels do not store a log-sum-exp), writes lse and D, then accumulates dQ over the KV blocks
-//                        the mask allows;
+//   attn_bwd_dq_kernel   one CTA per (sequence, query head, 64 query rows): ONE pass over the KV blocks the mask allows
+//                        — the row statistics are recomputed online (the forward kernels do not store a
+//                        log-sum-exp) and dQ accumulates against the running maximum, rescaled when it grows —
+//                        then writes lse and D for the other kernel;
 //   attn_bwd_dkv_kernel  one CTA per (sequence, KV head, 64 keys): loops over the query heads of the group and the
 //                        query blocks, works on the TRANSPOSED tiles (S^T = K Q^T, so P^T / dS^T come out directly in
 //                        the fragment layout the dV / dK products need) and accumulates dK, dV.
@@ -224,18 +225,34 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
     }
   };
 
-  // ---- pass 1: row statistics (online max / sum over the visited KV blocks)
+  // ---- ONE pass over the KV blocks the mask allows: the row statistics are accumulated online, as in the forward,
+  //      and so is dQ:   dQ_i = (1 / l_i) * sum_j exp2(s_ij - m_i) (dP_ij - D_i) K_j   with the running maximum in
+  //      place of m_i and the accumulator rescaled whenever it grows (exact: a common factor per row).  The first
+  //      version made a pass for (m, l) and a second one for dQ: a quarter more matrix products, twice the exponentials
+  //      and the K tiles fetched twice.
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float dq[KS * 2][4];
+#pragma unroll
+  for (int nt = 0; nt < KS * 2; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
   __syncthreads();   // every warp holds its Q / dO fragments and D: the four buffers are free
-  if (t_first <= t_last) bwd_tile_async<KS>(sT(0), kp, a.ks_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+  if (t_first <= t_last) {
+    bwd_tile_async<KS>(sT(0), kp, a.ks_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+    bwd_tile_async<KS>(sT(1), vp, a.vs_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
+  }
   cpasync_commit();
   for (int t = t_first, it = 0; t <= t_last; ++t, ++it) {
     cpasync_wait<0>();
     __syncthreads();   // block t has landed for everyone, and everyone is done with block t - 1
-    if (t < t_last) bwd_tile_async<KS>(sT((it + 1) & 1), kp, a.ks_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+    if (t < t_last) {
+      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1)), kp, a.ks_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1) + 1), vp, a.vs_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+    }
     cpasync_commit();
+    const __nv_bfloat16* sK = sT(2 * (it & 1));
+    const __nv_bfloat16* sV = sT(2 * (it & 1) + 1);
     float s[8][4];
-    scores(sT(it & 1), t * kBwdBN, s);
+    scores(sK, t * kBwdBN, s);
+    // ---- running maximum / sum, rescale of the accumulator
     float t0 = -INFINITY, t1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -248,57 +265,19 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
     t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
     const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
     const float r0 = n0 == -INFINITY ? 0.f : n0, r1 = n1 == -INFINITY ? 0.f : n1;
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      a0 += ex2(s[nt][0] - r0) + ex2(s[nt][1] - r0);
-      a1 += ex2(s[nt][2] - r1) + ex2(s[nt][3] - r1);
-    }
-    l0 = l0 * (m0 == -INFINITY ? 0.f : ex2(m0 - r0)) + a0;
-    l1 = l1 * (m1 == -INFINITY ? 0.f : ex2(m1 - r1)) + a1;
+    const float c0 = m0 == -INFINITY ? 0.f : ex2(m0 - r0), c1 = m1 == -INFINITY ? 0.f : ex2(m1 - r1);
     m0 = n0;
     m1 = n1;
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // scaled-log2 log-sum-exp; rows without any allowed key get +inf, so that exp2(s - lse) = 0 everywhere
-  const float lse0 = (l0 > 0.f) ? m0 + __log2f(l0) : INFINITY;
-  const float lse1 = (l1 > 0.f) ? m1 + __log2f(l1) : INFINITY;
-  if (tq == 0) {
-    if (i0 < a.Tq) {
-      P.lse[((long long)n * a.H + h) * a.Tq + i0] = lse0;
-      P.dsum[((long long)n * a.H + h) * a.Tq + i0] = D0;
-    }
-    if (i1 < a.Tq) {
-      P.lse[((long long)n * a.H + h) * a.Tq + i1] = lse1;
-      P.dsum[((long long)n * a.H + h) * a.Tq + i1] = D1;
-    }
-  }
-
-  // ---- pass 2: dQ += (P o (dO V^T - D)) K
-  float dq[KS * 2][4];
+    if (__any_sync(0xffffffffu, c0 != 1.f || c1 != 1.f)) {
 #pragma unroll
-  for (int nt = 0; nt < KS * 2; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
-  __syncthreads();   // pass 1 is done with its last block
-  if (t_first <= t_last) {
-    bwd_tile_async<KS>(sT(0), kp, a.ks_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
-    bwd_tile_async<KS>(sT(1), vp, a.vs_t, t_first * kBwdBN, a.Tk, a.hd, P.vec16);
-  }
-  cpasync_commit();
-  for (int t = t_first, it = 0; t <= t_last; ++t, ++it) {
-    cpasync_wait<0>();
-    __syncthreads();
-    if (t < t_last) {
-      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1)), kp, a.ks_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
-      bwd_tile_async<KS>(sT(2 * ((it + 1) & 1) + 1), vp, a.vs_t, (t + 1) * kBwdBN, a.Tk, a.hd, P.vec16);
+      for (int nt = 0; nt < KS * 2; ++nt) {
+        dq[nt][0] *= c0;
+        dq[nt][1] *= c0;
+        dq[nt][2] *= c1;
+        dq[nt][3] *= c1;
+      }
     }
-    cpasync_commit();
-    const __nv_bfloat16* sK = sT(2 * (it & 1));
-    const __nv_bfloat16* sV = sT(2 * (it & 1) + 1);
-    float s[8][4];
-    scores(sK, t * kBwdBN, s);
+    // ---- dP = dO V^T
     float dp[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
@@ -312,7 +291,8 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
         mma_bf16_16816(dp[np * 2 + 1], da[ks][0], da[ks][1], da[ks][2], da[ks][3], b[2], b[3]);
       }
     }
-    // dS in A-fragment form, one k-step (16 keys) per pair of n-tiles
+    // ---- p = exp2(s - m) (un-normalised), row sums, dS = p o (dP - D) in A-fragment form (one k-step per n-tile pair)
+    float a0 = 0.f, a1 = 0.f;
     uint32_t dsa[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -320,16 +300,22 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int nt = 2 * j + u;
-        d[u][0] = ex2(s[nt][0] - lse0) * (dp[nt][0] - D0);
-        d[u][1] = ex2(s[nt][1] - lse0) * (dp[nt][1] - D0);
-        d[u][2] = ex2(s[nt][2] - lse1) * (dp[nt][2] - D1);
-        d[u][3] = ex2(s[nt][3] - lse1) * (dp[nt][3] - D1);
+        const float p0 = ex2(s[nt][0] - r0), p1 = ex2(s[nt][1] - r0), p2 = ex2(s[nt][2] - r1), p3 = ex2(s[nt][3] - r1);
+        a0 += p0 + p1;
+        a1 += p2 + p3;
+        d[u][0] = p0 * (dp[nt][0] - D0);
+        d[u][1] = p1 * (dp[nt][1] - D0);
+        d[u][2] = p2 * (dp[nt][2] - D1);
+        d[u][3] = p3 * (dp[nt][3] - D1);
       }
       dsa[j][0] = pack_bf16x2(d[0][0], d[0][1]);
       dsa[j][1] = pack_bf16x2(d[0][2], d[0][3]);
       dsa[j][2] = pack_bf16x2(d[1][0], d[1][1]);
       dsa[j][3] = pack_bf16x2(d[1][2], d[1][3]);
     }
+    l0 = l0 * c0 + a0;
+    l1 = l1 * c1 + a1;
+    // ---- dQ += dS K
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -341,6 +327,24 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
       }
     }
   }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // scaled-log2 log-sum-exp for the dK/dV kernel; rows without any allowed key get +inf, so that exp2(s - lse) = 0
+  const float lse0 = (l0 > 0.f) ? m0 + __log2f(l0) : INFINITY;
+  const float lse1 = (l1 > 0.f) ? m1 + __log2f(l1) : INFINITY;
+  if (tq == 0) {
+    if (i0 < a.Tq) {
+      P.lse[((long long)n * a.H + h) * a.Tq + i0] = lse0;
+      P.dsum[((long long)n * a.H + h) * a.Tq + i0] = D0;
+    }
+    if (i1 < a.Tq) {
+      P.lse[((long long)n * a.H + h) * a.Tq + i1] = lse1;
+      P.dsum[((long long)n * a.H + h) * a.Tq + i1] = D1;
+    }
+  }
+  const float inv0 = l0 > 0.f ? P.scale / l0 : 0.f, inv1 = l1 > 0.f ? P.scale / l1 : 0.f;
   // ---- dQ * scale -> bf16 (dense [N, Tq, H, hd])
   __nv_bfloat16* dqp = P.dq + (((long long)n * a.Tq) * a.H + h) * a.hd;
 #pragma unroll
@@ -348,9 +352,9 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
     const int col = nt * 8 + tq * 2;
     if (col < a.hd) {
       if (i0 < a.Tq)
-        *reinterpret_cast<uint32_t*>(dqp + (long long)i0 * a.H * a.hd + col) = pack_bf16x2(dq[nt][0] * P.scale, dq[nt][1] * P.scale);
+        *reinterpret_cast<uint32_t*>(dqp + (long long)i0 * a.H * a.hd + col) = pack_bf16x2(dq[nt][0] * inv0, dq[nt][1] * inv0);
       if (i1 < a.Tq)
-        *reinterpret_cast<uint32_t*>(dqp + (long long)i1 * a.H * a.hd + col) = pack_bf16x2(dq[nt][2] * P.scale, dq[nt][3] * P.scale);
+        *reinterpret_cast<uint32_t*>(dqp + (long long)i1 * a.H * a.hd + col) = pack_bf16x2(dq[nt][2] * inv1, dq[nt][3] * inv1);
     }
   }
 }

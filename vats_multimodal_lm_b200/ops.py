@@ -222,8 +222,14 @@ def reset_decode_workspaces() -> None:
     _DECODE_WS.clear()
 
 
+_DECODE_WS_BYTES: dict = {}   # (device index, geometry) -> bytes: the C-ABI query is a ctypes call per decode step otherwise
+
+
 def _decode_workspace(device, stream: int, B: int, H: int, G: int, hd: int, S_max: int, left: int):
-    nbytes = max(_ffi.decode_workspace_bytes(B, H, G, hd, S_max, left), 16)
+    gkey = (device.index, B, H, G, hd, S_max, left)
+    nbytes = _DECODE_WS_BYTES.get(gkey)
+    if nbytes is None:
+        nbytes = _DECODE_WS_BYTES[gkey] = max(_ffi.decode_workspace_bytes(B, H, G, hd, S_max, left), 16)
     if torch.cuda.is_current_stream_capturing():
         return torch.zeros((nbytes,), dtype=torch.uint8, device=device), None
     key = (device.index, stream, B, H, G, hd, S_max, left)
