@@ -396,15 +396,31 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dkv_
   const int q_blocks = (a.Tq + kBwdBM - 1) / kBwdBM;
   // the (head of the group, query block) pairs with at least one allowed (query, key) pair against this key block, in
   // order; `advance` moves to the next one (every thread walks the same sequence)
+  auto pair_allowed = [&](int qb) -> bool {
+    int t_first, t_last;
+    tile_range(a.mask, qb * kBwdBM, kBwdBM, kBwdBN, &t_first, &t_last);
+    return (int)blockIdx.x >= t_first && (int)blockIdx.x <= t_last;
+  };
+  // the query blocks that can see this key block do not depend on the head: their span [qb_lo, qb_hi] is found once
+  // (a band mask leaves most of the q_blocks x hpg candidates out — walking all of them for every head was a fifth of
+  // the kernel's instructions on a 384-key window)
+  int qb_lo = q_blocks, qb_hi = -1;
+  for (int qb = 0; qb < q_blocks; ++qb) {
+    if (pair_allowed(qb)) {
+      if (qb < qb_lo) qb_lo = qb;
+      qb_hi = qb;
+    }
+  }
   auto advance = [&](int& hh, int& qb) -> bool {
+    if (qb_hi < qb_lo) return false;
     for (;;) {
-      if (++qb >= q_blocks) {
-        qb = 0;
+      if (qb < qb_lo) {
+        qb = qb_lo;
+      } else if (++qb > qb_hi) {
+        qb = qb_lo;
         if (++hh >= a.hpg) return false;
       }
-      int t_first, t_last;
-      tile_range(a.mask, qb * kBwdBM, kBwdBM, kBwdBN, &t_first, &t_last);
-      if ((int)blockIdx.x >= t_first && (int)blockIdx.x <= t_last) return true;
+      if (pair_allowed(qb)) return true;
     }
   };
   auto stage_pair = [&](int hh, int qb, int buf) {
