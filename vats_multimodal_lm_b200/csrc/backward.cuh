@@ -36,6 +36,8 @@ namespace vats {
 #endif
 constexpr int kBwdThreads = 128;
 constexpr int bwd_min_blocks(int ks) { return VATS_BWD_OCC ? (ks <= 4 ? 3 : (ks <= 6 ? 2 : 1)) : 1; }
+// (asking for 4 CTAs per SM in the dQ kernel — its 4-tile shared memory would allow it up to hd 64 — caps it at 128
+// registers, 124 bytes of spills, and measured the same 0.84 ms on the training step)
 constexpr int kBwdBM = 64;   // query rows per block
 constexpr int kBwdBN = 64;   // keys per block
 
@@ -54,9 +56,12 @@ struct BwdParams {
                                  // 16-byte cp.async copies (else 4-byte)
 };
 
-// dQ kernel: 4 tiles (Q / dO / O, then two K / V pairs); dK/dV kernel: 6 tiles (K, V, two Q / dO pairs) + two lse / D pairs
+// dQ kernel: 4 tiles (Q / dO / O, then two K / V pairs) + D; dK/dV kernel: 6 tiles (K, V, two Q / dO pairs) + two lse / D pairs
 __host__ __device__ inline size_t bwd_smem_bytes(int hd_pad) {
   return (size_t)6 * kBwdBM * (hd_pad + 8) * 2 + 4 * kBwdBM * sizeof(float);
+}
+__host__ __device__ inline size_t bwd_dq_smem_bytes(int hd_pad) {
+  return (size_t)4 * kBwdBM * (hd_pad + 8) * 2 + kBwdBM * sizeof(float);
 }
 
 // rows [row0, row0 + 64) x hd of a row-strided bf16 matrix -> smem tile [64][KS * 16 + 8], asynchronously: cp.async copies
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(kBwdThreads, bwd_min_blocks(KS)) attn_bwd_dq_k
   auto sT = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(bwd_smem) + i * kBwdBM * pitch; };
   __nv_bfloat16* sQ = sT(0);
   __nv_bfloat16* sdO = sT(1);
-  float* sD = reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(bwd_smem) + 6 * kBwdBM * pitch);
+  float* sD = reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(bwd_smem) + 4 * kBwdBM * pitch);
 
   const int q0 = blockIdx.x * kBwdBM, h = blockIdx.y, n = blockIdx.z;
   const int g = h / a.hpg;

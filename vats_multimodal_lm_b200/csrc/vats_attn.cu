@@ -1105,6 +1105,7 @@ int vats_attn_prefill_backward(const void* q, const void* k, const void* v, cons
     P.vec16 = (al16(A.q, A.qs) && al16(A.k, A.ks) && al16(A.v, A.vs) && al16(A.o, A.os) && al16(dout, do_strides)) ? 1 : 0;
   }
   const size_t smem = vats::bwd_smem_bytes(P.hd_pad);
+  const size_t smem_dq = vats::bwd_dq_smem_bytes(P.hd_pad);
   const int ks = P.hd_pad / 16;
   const dim3 grid_q((Tq + vats::kBwdBM - 1) / vats::kBwdBM, H, N);
   const dim3 grid_k((Tk + vats::kBwdBN - 1) / vats::kBwdBN, G, N);
@@ -1115,9 +1116,9 @@ int vats_attn_prefill_backward(const void* q, const void* k, const void* v, cons
 #define VATS_BWD_CASE(KS)                                                                                         \
   case KS: {                                                                                                      \
     static thread_local SmemAttrCache c1, c2;                                                                     \
-    CUDA_TRY(ensure_dyn_smem(vats::attn_bwd_dq_kernel<KS>, smem, c1));                                            \
+    CUDA_TRY(ensure_dyn_smem(vats::attn_bwd_dq_kernel<KS>, smem_dq, c1));                                            \
     CUDA_TRY(ensure_dyn_smem(vats::attn_bwd_dkv_kernel<KS>, smem, c2));                                           \
-    if (Tq > 0) vats::attn_bwd_dq_kernel<KS><<<grid_q, vats::kBwdThreads, smem, st>>>(P);                         \
+    if (Tq > 0) vats::attn_bwd_dq_kernel<KS><<<grid_q, vats::kBwdThreads, smem_dq, st>>>(P);                         \
     vats::attn_bwd_dkv_kernel<KS><<<grid_k, vats::kBwdThreads, smem, st>>>(P);                                    \
   } break;
   switch (ks) {
