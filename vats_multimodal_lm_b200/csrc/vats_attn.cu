@@ -935,6 +935,7 @@ int launch_decode_mma(vats::DecodeMmaParams& P, const CUtensorMap& mk, const CUt
   while (vats::decode_mma_smem_bytes<HD, NCW, SK>(max_stages) > 227 * 1024 && max_stages > 2) --max_stages;
   // Tiles of <= 64 columns (hd 60 / 64: 8 KB stages) take three stages per consumer warp: cfg2-medium 8 stages 0.135,
   // 12 stages 0.129, 16 stages 0.138, 24 stages 0.143 ms (tools/run_workload.py cfg2m --time, launch latency included).
+  // (64-key stages for these tiles — 16 KB per stage like a 128-column tile's — measured 0.118 against 0.114 ms.)
   const int want_stages = (HD <= 64 ? 3 : 2) * NCW;
   int stages = want_stages < max_stages ? want_stages : max_stages;
   if (const char* e = getenv("VATS_DECODE_STAGES")) {  // tuning / debugging knob
